@@ -1,0 +1,61 @@
+// ert_common.cuh -- device-side configuration shared by the libertgpu kernels.
+//
+// Geometry names follow protocol.PacketConfig (reference protocol/decode.go:27-42):
+// CL=ChipLength, SL=SymbolLength, BS=BlockSize, PS/PK=Preamble/PacketSymbols,
+// PL/PKL=Preamble/PacketLength, BUF=BufferLength.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ertgpu.h"
+
+namespace ert {
+
+struct DevProto {
+    int32_t preamble_id;
+    int32_t check_kind;
+    int32_t packet_bytes;  // this parser's own (PacketSymbols+7)>>3
+    int32_t crc_from, crc_to;
+    uint16_t crc_init, crc_residue;
+    int32_t table;  // index into the CRC table array
+};
+
+struct DevCfg {
+    int32_t CL, SL, BS, PS, PK, PL, PKL, BUF;
+    int32_t words_per_block;  // BS/32
+    int32_t hist_words;       // ceil(PKL/32): bit-plane history kept in front of a call's bits
+    int32_t hist_samples;     // IQ history kept in front of a call's samples (= PKL)
+    int32_t packet_bytes;     // (PK+7)>>3
+    int32_t npre;
+    int32_t pre_nbits[ERTGPU_MAX_PROTOCOLS];
+    uint8_t pre_bits[ERTGPU_MAX_PROTOCOLS][ERTGPU_MAX_PREAMBLE];
+    int32_t pre_has_r900[ERTGPU_MAX_PROTOCOLS];
+    int32_t nproto;
+    DevProto proto[ERTGPU_MAX_PROTOCOLS];
+};
+
+// A search hit before slicing: start position (in samples) relative to
+// (first global sample of the call) - PKL, and the preamble that matched.
+struct RawHit {
+    unsigned long long s;
+    int32_t preamble_id;
+    int32_t pad;
+};
+
+// Plane bit order: stream bit g lives in word g>>5 at bit position 31-(g&31)
+// (MSB first, like the reference's packed bytes, decode.go:259-265).
+__device__ __forceinline__ uint32_t plane_bit(const uint32_t* __restrict__ plane, long long pos) {
+    return (plane[pos >> 5] >> (31 - (int)(pos & 31))) & 1u;
+}
+
+// 32 consecutive plane bits starting at bit `pos`, first bit in the MSB.
+__device__ __forceinline__ uint32_t plane_window(const uint32_t* __restrict__ plane, long long pos) {
+    long long w = pos >> 5;
+    int sh = (int)(pos & 31);
+    uint32_t hi = plane[w];
+    if (sh == 0) return hi;
+    return __funnelshift_l(plane[w + 1], hi, sh);
+}
+
+}  // namespace ert

@@ -1,0 +1,725 @@
+// ertgpu.cu -- C ABI of libertgpu.so (see include/ertgpu.h) and the host-side pipeline that
+// drives the sm_100a kernels.  One handle mirrors one reference protocol.Decoder
+// (protocol/decode.go:45-63).
+//
+// Device data layout (all per handle):
+//   iq      : the call's interleaved uint8 I,Q bytes (caller's device buffer or a staging chunk)
+//   hist[2] : last PKL samples of the previous call (ping-pong) -- replaces the Signal tail
+//             (decode.go:165) and the r900 parser's private signal history (r900.go:169)
+//   plane[2]: packed quantizer output, 1 bit per sample, MSB first, laid out as
+//             [hist_words of history | BS/32 words per block of the call] (ping-pong) --
+//             replaces Decoder.Quantized (1 byte per bit) and Decoder.packed
+//   hits    : (start, preamble) pairs found by search_kernel
+//   out     : ertgpu_candidate records produced by extract_kernel
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "demod_fast.cuh"
+#include "demod_generic.cuh"
+#include "ert_common.cuh"
+#include "search.cuh"
+#include "synth.cuh"
+
+using namespace ert;
+
+struct ertgpu_handle {
+    std::string err;
+    std::vector<ertgpu_protocol> protos;
+    ertgpu_decoder_config cfg{};
+    bool allocated = false;
+    int device = 0;
+
+    DevCfg dcfg{};
+    Gf32 gf{};
+    float h_lut[256];
+
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+
+    float* d_lut = nullptr;
+    uint16_t* d_crc = nullptr;
+    uint32_t* d_plane[2] = {nullptr, nullptr};
+    size_t plane_words = 0;
+    int cur_plane = 0;
+    uint8_t* d_hist[2] = {nullptr, nullptr};
+    int cur_hist = 0;
+    int hist_valid = 0;
+    uint8_t* d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    RawHit* d_hits = nullptr;
+    uint8_t* d_digits = nullptr;
+    ertgpu_candidate* d_out = nullptr;
+    unsigned long long cand_cap = 0;
+    unsigned long long* d_counters = nullptr;  // [0]=hits [1]=out [2]=valid
+    unsigned long long* h_counters = nullptr;  // pinned mirror
+    float* d_tap = nullptr;                    // scratch for taps
+    size_t tap_floats = 0;
+
+    int64_t max_blocks = 0;
+    int64_t block_counter = 0;  // number of reference Decode calls consumed so far
+    bool has_r900 = false;
+    int demod_variant = 0;      // 0 generic, else specialised chip length
+
+    // state of the last enqueued pipeline (for fetch and taps)
+    bool pending = false;
+    cudaStream_t pending_stream = nullptr;
+    const uint8_t* last_iq = nullptr;
+    const uint8_t* last_hist = nullptr;
+    int last_hist_valid = 0;
+    const uint32_t* last_plane = nullptr;
+    int64_t last_first_block = 0, last_nblocks = 0;
+    bool overflow = false;
+    unsigned long long need = 0;
+    int64_t total_hits = 0, total_valid = 0;
+    int64_t launches = 0;
+    std::vector<ertgpu_candidate> results;
+};
+
+namespace {
+
+int fail(ertgpu_handle* h, int code, const char* fmt, ...) {
+    if (h) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        h->err = buf;
+    }
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                       \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            cudaGetLastError();                                                                 \
+            return fail(h, e__ == cudaErrorMemoryAllocation ? ERTGPU_ENOMEM : ERTGPU_ECUDA,     \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                       \
+    } while (0)
+
+// decode.go:377-379
+int32_t next_pow2(int32_t v) {
+    int32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// decode.go:209-216 -- computed on the host with IEEE float32 division and multiplication
+void make_maglut(float* lut) {
+    for (int i = 0; i < 256; i++) {
+        volatile float x = (127.5f - (float)i) / 127.5f;
+        volatile float y = x * x;
+        lut[i] = y;
+    }
+}
+
+// crc.go:34-47
+void make_crc_table(uint16_t poly, uint16_t* t) {
+    for (int i = 0; i < 256; i++) {
+        uint16_t crc = (uint16_t)(i << 8);
+        for (int b = 0; b < 8; b++) crc = (crc & 0x8000) ? (uint16_t)((crc << 1) ^ poly) : (uint16_t)(crc << 1);
+        t[i] = crc;
+    }
+}
+
+// gf.go:20-57 for NewField(32, 37, 2)
+void make_gf32(Gf32* g) {
+    int x = 1;
+    for (int i = 0; i < 31; i++) {
+        g->exp[i] = g->exp[i + 31] = (uint8_t)x;
+        g->log[x] = (uint8_t)i;
+        x <<= 1;
+        if (x & 32) x ^= 37;
+    }
+    g->log[0] = 31;
+}
+
+void free_device(ertgpu_handle* h) {
+    if (!h->allocated) return;
+    cudaSetDevice(h->device);
+    for (int k = 0; k < 2; k++) {
+        cudaFree(h->d_plane[k]);
+        cudaFree(h->d_hist[k]);
+        cudaFree(h->d_stage[k]);
+        if (h->ev_h2d[k]) cudaEventDestroy(h->ev_h2d[k]);
+        if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
+    }
+    cudaFree(h->d_lut);
+    cudaFree(h->d_crc);
+    cudaFree(h->d_hits);
+    cudaFree(h->d_digits);
+    cudaFree(h->d_out);
+    cudaFree(h->d_counters);
+    cudaFree(h->d_tap);
+    if (h->h_counters) cudaFreeHost(h->h_counters);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    h->allocated = false;
+}
+
+// Enqueue the whole per-call pipeline for `nblocks` blocks whose IQ bytes are at d_iq.
+int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uint32_t flags,
+                     cudaStream_t st) {
+    const DevCfg& c = h->dcfg;
+    uint32_t* plane = h->d_plane[h->cur_plane];
+    uint32_t* plane_next = h->d_plane[h->cur_plane ^ 1];
+    const uint8_t* hist = h->d_hist[h->cur_hist];
+    uint8_t* hist_next = h->d_hist[h->cur_hist ^ 1];
+    const long long nwords = nblocks * c.words_per_block;
+    const long long p0 = (long long)c.hist_words * 32 - c.PKL;
+    h->launches = 0;
+
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, 3 * sizeof(unsigned long long), st));
+
+    // 1. magnitude + matched filter + quantize + pack
+    if (h->demod_variant != 0) {
+        int rc = launch_demod_fast(h->demod_variant, d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut,
+                                   plane + c.hist_words, nblocks, c.BS, st);
+        if (rc != 0) return fail(h, ERTGPU_ECUDA, "demod_fast launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    } else {
+        int nthr = 128;
+        while (nthr > 32 && (256 + 2 * (size_t)c.CL * nthr) * sizeof(float) > 200 * 1024) nthr >>= 1;
+        const size_t smem = (256 + 2 * (size_t)c.CL * nthr) * sizeof(float);
+        if (smem > 227 * 1024) return fail(h, ERTGPU_EINVAL, "chip length %d too large for the generic kernel", c.CL);
+        CUDA_TRY(h, cudaFuncSetAttribute(demod_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)((nblocks + nthr - 1) / nthr);
+        demod_generic_kernel<<<grid, nthr, smem, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut,
+                                                       plane + c.hist_words, nblocks, c.BS, c.CL);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    h->launches++;
+
+    // 2. preamble search over every start position of the call
+    {
+        const int nthr = 256;
+        long long blocks = (nwords + nthr - 1) / nthr;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        if (blocks < 1) blocks = 1;
+        search_kernel<<<(unsigned)blocks, nthr, 0, st>>>(plane, p0, nwords, c, h->d_hits, h->cand_cap, h->d_counters);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches++;
+    }
+
+    // 3. r900 payload digits for hits of an r900 preamble
+    const uint8_t* digits = nullptr;
+    if (h->has_r900) {
+        r900_replay_kernel<<<148, 64, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c, h->d_hits,
+                                               h->cand_cap, h->d_counters, h->d_digits);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches++;
+        digits = h->d_digits;
+    }
+
+    // 4. slice + integrity screens
+    extract_kernel<<<148 * 4, 96, 0, st>>>(plane, p0, c, h->d_hits, h->cand_cap, h->d_counters, h->d_crc, h->gf,
+                                           digits, h->block_counter, flags, h->d_out, h->cand_cap,
+                                           h->d_counters + 1, h->d_counters + 2);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+
+    // 5. carry history to the other buffers
+    carry_kernel<<<64, 256, 0, st>>>(plane, plane_next, nwords, c.hist_words, d_iq, hist, hist_next, c.hist_samples,
+                                     nblocks * c.BS);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+
+    h->last_iq = d_iq;
+    h->last_hist = hist;
+    h->last_hist_valid = h->hist_valid;
+    h->last_plane = plane;
+    h->last_first_block = h->block_counter;
+    h->last_nblocks = nblocks;
+    h->pending = true;
+    h->pending_stream = st;
+
+    h->cur_plane ^= 1;
+    h->cur_hist ^= 1;
+    long long hv = (long long)h->hist_valid + nblocks * c.BS;
+    h->hist_valid = (int)std::min<long long>(hv, c.hist_samples);
+    h->block_counter += nblocks;
+    return ERTGPU_OK;
+}
+
+// Wait for the pending pipeline and append its candidates to h->results.
+int collect(ertgpu_handle* h) {
+    if (!h->pending) return ERTGPU_OK;
+    CUDA_TRY(h, cudaStreamSynchronize(h->pending_stream));
+    h->pending = false;
+    const unsigned long long nh = h->h_counters[0], no = h->h_counters[1], nv = h->h_counters[2];
+    h->total_hits += (int64_t)nh;
+    h->total_valid += (int64_t)nv;
+    if (nh > h->cand_cap) {
+        h->overflow = true;
+        h->need = std::max(h->need, nh);
+    }
+    const unsigned long long take = std::min(no, h->cand_cap);
+    if (take) {
+        const size_t old = h->results.size();
+        h->results.resize(old + take);
+        CUDA_TRY(h, cudaMemcpy(h->results.data() + old, h->d_out, take * sizeof(ertgpu_candidate), cudaMemcpyDeviceToHost));
+    }
+    return ERTGPU_OK;
+}
+
+bool cand_less(const ertgpu_candidate& a, const ertgpu_candidate& b) {
+    if (a.block != b.block) return a.block < b.block;
+    if (a.preamble_id != b.preamble_id) return a.preamble_id < b.preamble_id;
+    return a.idx < b.idx;
+}
+
+int deliver(ertgpu_handle* h, ertgpu_candidate* out, size_t cap, size_t* n_out) {
+    if (h->overflow) {
+        if (n_out) *n_out = (size_t)h->need;
+        return fail(h, ERTGPU_ECAPACITY, "internal candidate capacity %llu exceeded (%llu hits): allocate with a larger max_candidates",
+                    h->cand_cap, h->need);
+    }
+    std::sort(h->results.begin(), h->results.end(), cand_less);
+    if (n_out) *n_out = h->results.size();
+    if (h->results.size() > cap) return fail(h, ERTGPU_ECAPACITY, "output array holds %zu candidates, %zu needed", cap, h->results.size());
+    if (!h->results.empty() && out) memcpy(out, h->results.data(), h->results.size() * sizeof(ertgpu_candidate));
+    return ERTGPU_OK;
+}
+
+void begin_call(ertgpu_handle* h) {
+    h->results.clear();
+    h->overflow = false;
+    h->need = 0;
+    h->total_hits = h->total_valid = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ertgpu_abi_version(void) { return ERTGPU_ABI_VERSION; }
+
+const char* ertgpu_last_error(const ertgpu_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int ertgpu_create(ertgpu_handle** out) {
+    if (!out) return ERTGPU_EINVAL;
+    ertgpu_handle* h = new (std::nothrow) ertgpu_handle();
+    if (!h) return ERTGPU_ENOMEM;
+    *out = h;
+    return ERTGPU_OK;
+}
+
+void ertgpu_destroy(ertgpu_handle* h) {
+    if (!h) return;
+    free_device(h);
+    delete h;
+}
+
+int ertgpu_stock_protocol(const char* msgtype, int32_t chip_length, ertgpu_protocol* p) {
+    if (!msgtype || !p) return ERTGPU_EINVAL;
+    memset(p, 0, sizeof(*p));
+    p->data_rate = 32768;
+    p->chip_length = chip_length;
+    p->center_freq = 912600155u;
+    snprintf(p->name, sizeof(p->name), "%s", msgtype);
+    if (!strcmp(msgtype, "scm")) {  // scm/scm.go:40-50
+        snprintf(p->preamble, sizeof(p->preamble), "%s", "111110010101001100000");
+        p->preamble_symbols = 21;
+        p->packet_symbols = 96;
+        p->check_kind = ERTGPU_CHECK_CRC16;
+        p->crc_init = 0; p->crc_poly = 0x6F63; p->crc_residue = 0;
+        p->crc_from = 2; p->crc_to = 12;
+    } else if (!strcmp(msgtype, "scm+")) {  // scmplus/scmplus.go:47-57
+        snprintf(p->preamble, sizeof(p->preamble), "%s", "0001011010100011");
+        p->preamble_symbols = 16;
+        p->packet_symbols = 128;
+        p->check_kind = ERTGPU_CHECK_CRC16;
+        p->crc_init = 0xFFFF; p->crc_poly = 0x1021; p->crc_residue = 0x1D0F;
+        p->crc_from = 2; p->crc_to = 16;
+    } else if (!strcmp(msgtype, "idm") || !strcmp(msgtype, "netidm")) {  // idm/idm.go:46-56, netidm/netidm.go:58-68
+        snprintf(p->preamble, sizeof(p->preamble), "%s", "01010101010101010001011010100011");
+        p->preamble_symbols = 32;
+        p->packet_symbols = 92 * 8;
+        p->check_kind = ERTGPU_CHECK_IDM;
+        p->crc_init = 0xFFFF; p->crc_poly = 0x1021; p->crc_residue = 0x1D0F;
+        p->crc_from = 4; p->crc_to = 92;
+    } else if (!strcmp(msgtype, "r900") || !strcmp(msgtype, "r900bcd")) {  // r900/r900.go:54-65
+        snprintf(p->preamble, sizeof(p->preamble), "%s", "00000000000000001110010101100100");
+        p->preamble_symbols = 32;
+        p->packet_symbols = 116;
+        p->center_freq = 912380000u;
+        p->check_kind = ERTGPU_CHECK_R900;
+    } else {
+        return ERTGPU_EINVAL;  // parse.go:49 "invalid message type"
+    }
+    return ERTGPU_OK;
+}
+
+int ertgpu_register_protocol(ertgpu_handle* h, const ertgpu_protocol* p) {
+    if (!h || !p) return ERTGPU_EINVAL;
+    if (h->allocated) return fail(h, ERTGPU_EINVAL, "register_protocol after allocate");
+    if (h->protos.size() >= ERTGPU_MAX_PROTOCOLS) return fail(h, ERTGPU_EINVAL, "too many protocols");
+    const size_t n = strnlen(p->preamble, sizeof(p->preamble));
+    if (n == 0 || n > ERTGPU_MAX_PREAMBLE) return fail(h, ERTGPU_EINVAL, "bad preamble length %zu", n);
+    for (size_t i = 0; i < n; i++)
+        if (p->preamble[i] != '0' && p->preamble[i] != '1') return fail(h, ERTGPU_EINVAL, "preamble must be '0'/'1'");
+    if (p->chip_length <= 0 || p->preamble_symbols <= 0 || p->packet_symbols <= 0)
+        return fail(h, ERTGPU_EINVAL, "non-positive geometry");
+    if ((p->packet_symbols + 7) / 8 > ERTGPU_MAX_PACKET_BYTES) return fail(h, ERTGPU_EINVAL, "packet too long");
+    if (p->check_kind == ERTGPU_CHECK_CRC16 &&
+        (p->crc_from < 0 || p->crc_to > (p->packet_symbols + 7) / 8 || p->crc_from >= p->crc_to))
+        return fail(h, ERTGPU_EINVAL, "bad crc range");
+    if (p->check_kind == ERTGPU_CHECK_IDM && p->packet_symbols < 92 * 8) return fail(h, ERTGPU_EINVAL, "idm screen needs 92 bytes");
+    h->protos.push_back(*p);
+    // decode.go:105-109
+    ertgpu_decoder_config& c = h->cfg;
+    c.center_freq = p->center_freq;
+    c.data_rate = std::max(c.data_rate, p->data_rate);
+    c.chip_length = std::max(c.chip_length, p->chip_length);
+    c.preamble_symbols = std::max(c.preamble_symbols, p->preamble_symbols);
+    c.packet_symbols = std::max(c.packet_symbols, p->packet_symbols);
+    c.n_protocols = (int32_t)h->protos.size();
+    return ERTGPU_OK;
+}
+
+int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_call, int64_t max_candidates) {
+    if (!h) return ERTGPU_EINVAL;
+    if (h->allocated) return fail(h, ERTGPU_EINVAL, "already allocated");
+    if (h->protos.empty()) return fail(h, ERTGPU_EINVAL, "no protocol registered");
+
+    // decode.go:131-141
+    ertgpu_decoder_config& c = h->cfg;
+    c.symbol_length = c.chip_length << 1;
+    c.sample_rate = c.data_rate * c.chip_length;
+    c.preamble_length = c.preamble_symbols * c.symbol_length;
+    c.packet_length = c.packet_symbols * c.symbol_length;
+    c.block_size = next_pow2(c.preamble_length);
+    c.block_size2 = c.block_size << 1;
+    c.buffer_length = c.packet_length + c.block_size;
+    c.packet_bytes = (c.packet_symbols + 7) >> 3;
+    if (c.block_size < 32) return fail(h, ERTGPU_EINVAL, "block size %d below 32", c.block_size);
+
+    DevCfg& d = h->dcfg;
+    memset(&d, 0, sizeof(d));
+    d.CL = c.chip_length; d.SL = c.symbol_length; d.BS = c.block_size;
+    d.PS = c.preamble_symbols; d.PK = c.packet_symbols;
+    d.PL = c.preamble_length; d.PKL = c.packet_length; d.BUF = c.buffer_length;
+    d.words_per_block = d.BS / 32;
+    d.hist_words = (d.PKL + 31) / 32;
+    d.hist_samples = d.PKL;
+    d.packet_bytes = c.packet_bytes;
+    d.nproto = (int32_t)h->protos.size();
+    std::vector<uint16_t> tables;
+    h->has_r900 = false;
+    for (int i = 0; i < d.nproto; i++) {
+        const ertgpu_protocol& p = h->protos[i];
+        const int nb = (int)strnlen(p.preamble, sizeof(p.preamble));
+        int found = -1;
+        for (int j = 0; j < d.npre; j++) {
+            if (d.pre_nbits[j] != nb) continue;
+            bool same = true;
+            for (int k = 0; k < nb; k++) same = same && d.pre_bits[j][k] == (uint8_t)(p.preamble[k] == '1');
+            if (same) found = j;
+        }
+        if (found < 0) {  // decode.go:121-124
+            found = d.npre++;
+            d.pre_nbits[found] = nb;
+            for (int k = 0; k < nb; k++) d.pre_bits[found][k] = (uint8_t)(p.preamble[k] == '1');
+        }
+        DevProto& dp = d.proto[i];
+        dp.preamble_id = found;
+        dp.check_kind = p.check_kind;
+        dp.packet_bytes = (p.packet_symbols + 7) >> 3;
+        dp.crc_from = p.crc_from; dp.crc_to = p.crc_to;
+        dp.crc_init = p.crc_init; dp.crc_residue = p.crc_residue;
+        dp.table = i;
+        tables.resize((size_t)(i + 1) * 256);
+        make_crc_table(p.crc_poly, tables.data() + (size_t)i * 256);
+        if (p.check_kind == ERTGPU_CHECK_R900) {
+            d.pre_has_r900[found] = 1;
+            h->has_r900 = true;
+        }
+    }
+    c.n_preambles = d.npre;
+
+    int ndev = 0;
+    CUDA_TRY(h, cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(h, ERTGPU_ECUDA, "device %d not available (%d devices)", device, ndev);
+    h->device = device;
+    CUDA_TRY(h, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(h, ERTGPU_ECUDA, "libertgpu is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+
+    if (max_blocks_per_call <= 0) max_blocks_per_call = std::max<int64_t>(1, (64ll << 20) / c.block_size2);
+    if (max_candidates <= 0) max_candidates = 1 << 18;
+    h->max_blocks = max_blocks_per_call;
+    h->cand_cap = (unsigned long long)max_candidates;
+    h->allocated = true;  // from here free_device() cleans up on failure
+
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_h2d[k], cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
+    }
+    make_maglut(h->h_lut);
+    make_gf32(&h->gf);
+    CUDA_TRY(h, cudaMalloc(&h->d_lut, 256 * sizeof(float)));
+    CUDA_TRY(h, cudaMemcpy(h->d_lut, h->h_lut, 256 * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMalloc(&h->d_crc, tables.size() * sizeof(uint16_t)));
+    CUDA_TRY(h, cudaMemcpy(h->d_crc, tables.data(), tables.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+
+    h->plane_words = (size_t)d.hist_words + (size_t)max_blocks_per_call * d.words_per_block + 8;
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(h, cudaMalloc(&h->d_plane[k], h->plane_words * sizeof(uint32_t)));
+        CUDA_TRY(h, cudaMemset(h->d_plane[k], 0, h->plane_words * sizeof(uint32_t)));
+        CUDA_TRY(h, cudaMalloc(&h->d_hist[k], (size_t)d.hist_samples * 2 + 16));
+        CUDA_TRY(h, cudaMemset(h->d_hist[k], 0, (size_t)d.hist_samples * 2 + 16));
+    }
+    CUDA_TRY(h, cudaMalloc(&h->d_hits, h->cand_cap * sizeof(RawHit)));
+    CUDA_TRY(h, cudaMalloc(&h->d_out, h->cand_cap * sizeof(ertgpu_candidate)));
+    if (h->has_r900) CUDA_TRY(h, cudaMalloc(&h->d_digits, h->cand_cap * ERTGPU_R900_DIGITS));
+    CUDA_TRY(h, cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaHostAlloc(&h->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    h->tap_floats = (size_t)std::max(d.BS + d.SL, d.BUF) * 2 + 16;
+    CUDA_TRY(h, cudaMalloc(&h->d_tap, h->tap_floats * sizeof(float)));
+
+    h->demod_variant = demod_fast_variant(d.CL, d.BS);
+    h->cur_plane = h->cur_hist = 0;
+    h->hist_valid = 0;
+    h->block_counter = 0;
+    return ERTGPU_OK;
+}
+
+int ertgpu_get_config(const ertgpu_handle* h, ertgpu_decoder_config* cfg) {
+    if (!h || !cfg) return ERTGPU_EINVAL;
+    if (!h->allocated) return ERTGPU_EINVAL;
+    *cfg = h->cfg;
+    return ERTGPU_OK;
+}
+
+int ertgpu_reset(ertgpu_handle* h) {
+    if (!h || !h->allocated) return ERTGPU_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->pending) {
+        CUDA_TRY(h, cudaStreamSynchronize(h->pending_stream));
+        h->pending = false;
+    }
+    // only the history in front of the next call has to read as zeros (decode.go:144-145)
+    for (int k = 0; k < 2; k++)
+        CUDA_TRY(h, cudaMemsetAsync(h->d_plane[k], 0, (size_t)h->dcfg.hist_words * sizeof(uint32_t), h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->hist_valid = 0;
+    h->block_counter = 0;
+    begin_call(h);
+    return ERTGPU_OK;
+}
+
+int ertgpu_set_demod_variant(ertgpu_handle* h, int32_t variant) {
+    // test hook: 0 forces the generic kernel, -1 restores the automatic choice
+    if (!h || !h->allocated) return ERTGPU_EINVAL;
+    if (variant < 0) h->demod_variant = demod_fast_variant(h->dcfg.CL, h->dcfg.BS);
+    else if (variant == 0) h->demod_variant = 0;
+    else return ERTGPU_EINVAL;
+    return ERTGPU_OK;
+}
+
+int ertgpu_decode_device_async(ertgpu_handle* h, const void* d_iq, size_t nbytes, uint32_t flags, void* stream) {
+    if (!h || !h->allocated) return ERTGPU_EINVAL;
+    if (!d_iq && nbytes) return fail(h, ERTGPU_EINVAL, "null input");
+    if ((reinterpret_cast<uintptr_t>(d_iq) & 15) != 0) return fail(h, ERTGPU_EINVAL, "device input must be 16-byte aligned");
+    const size_t bs2 = (size_t)h->cfg.block_size2;
+    if (nbytes % bs2) return fail(h, ERTGPU_ESIZE, "nbytes %zu is not a multiple of BlockSize2 %zu", nbytes, bs2);
+    const int64_t nblocks = (int64_t)(nbytes / bs2);
+    if (nblocks > h->max_blocks) return fail(h, ERTGPU_ESIZE, "%lld blocks exceed max_blocks_per_call %lld", (long long)nblocks, (long long)h->max_blocks);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->pending) {
+        int rc = collect(h);
+        if (rc) return rc;
+    }
+    begin_call(h);
+    if (nblocks == 0) return ERTGPU_OK;
+    return enqueue_pipeline(h, static_cast<const uint8_t*>(d_iq), nblocks, flags, stream ? (cudaStream_t)stream : h->stream);
+}
+
+int ertgpu_fetch(ertgpu_handle* h, ertgpu_candidate* out, size_t cap, size_t* n_out) {
+    if (!h || !h->allocated) return ERTGPU_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = collect(h);
+    if (rc) return rc;
+    return deliver(h, out, cap, n_out);
+}
+
+int ertgpu_decode(ertgpu_handle* h, const uint8_t* iq, size_t nbytes, uint32_t flags, ertgpu_candidate* out,
+                  size_t cap, size_t* n_out) {
+    if (!h || !h->allocated) return ERTGPU_EINVAL;
+    if (!iq && nbytes) return fail(h, ERTGPU_EINVAL, "null input");
+    const size_t bs2 = (size_t)h->cfg.block_size2;
+    if (nbytes % bs2) return fail(h, ERTGPU_ESIZE, "nbytes %zu is not a multiple of BlockSize2 %zu", nbytes, bs2);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->pending) {
+        int rc = collect(h);
+        if (rc) return rc;
+    }
+    begin_call(h);
+    const int64_t nblocks = (int64_t)(nbytes / bs2);
+    if (nblocks == 0) return deliver(h, out, cap, n_out);
+
+    // staging chunks (allocated on first use): H2D of chunk i+1 overlaps the kernels of chunk i
+    const int64_t chunk_blocks = std::min<int64_t>(h->max_blocks, std::max<int64_t>(1, (32ll << 20) / (int64_t)bs2));
+    if (h->stage_bytes < (size_t)chunk_blocks * bs2) {
+        for (int k = 0; k < 2; k++) {
+            cudaFree(h->d_stage[k]);
+            h->d_stage[k] = nullptr;
+        }
+        h->stage_bytes = (size_t)chunk_blocks * bs2;
+        for (int k = 0; k < 2; k++) CUDA_TRY(h, cudaMalloc(&h->d_stage[k], h->stage_bytes));
+    }
+    int64_t done = 0, launches = 0;
+    for (int64_t i = 0; done < nblocks; i++) {
+        const int k = (int)(i & 1);
+        const int64_t nb = std::min(chunk_blocks, nblocks - done);
+        if (i >= 2) CUDA_TRY(h, cudaEventSynchronize(h->ev_done[k]));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_stage[k], iq + (size_t)done * bs2, (size_t)nb * bs2, cudaMemcpyHostToDevice, h->copy_stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_h2d[k], h->copy_stream));
+        if (i >= 1) {
+            int rc = collect(h);
+            if (rc) return rc;
+        }
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_h2d[k], 0));
+        int rc = enqueue_pipeline(h, h->d_stage[k], nb, flags, h->stream);
+        if (rc) return rc;
+        launches += h->launches;
+        CUDA_TRY(h, cudaEventRecord(h->ev_done[k], h->stream));
+        done += nb;
+    }
+    int rc = collect(h);
+    if (rc) return rc;
+    h->launches = launches;
+    return deliver(h, out, cap, n_out);
+}
+
+int ertgpu_last_counts(ertgpu_handle* h, int64_t* n_candidates, int64_t* n_valid) {
+    if (!h || !h->allocated) return ERTGPU_EINVAL;
+    if (h->pending) {
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        int rc = collect(h);
+        if (rc) return rc;
+    }
+    if (n_candidates) *n_candidates = h->total_hits;
+    if (n_valid) *n_valid = h->total_valid;
+    return ERTGPU_OK;
+}
+
+int64_t ertgpu_last_launches(const ertgpu_handle* h) { return h ? h->launches : 0; }
+
+int ertgpu_tap(ertgpu_handle* h, int32_t which, int64_t block, void* dst, size_t cap, size_t* n_out) {
+    if (!h || !h->allocated) return ERTGPU_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->pending) {
+        int rc = collect(h);
+        if (rc) return rc;
+    }
+    if (!h->last_plane) return fail(h, ERTGPU_EINVAL, "no decode call yet");
+    const DevCfg& c = h->dcfg;
+    const int64_t b = block - h->last_first_block;
+    if (b < 0 || b >= h->last_nblocks) return fail(h, ERTGPU_EINVAL, "block %lld outside the last (chunk of the) call [%lld,%lld)",
+                                                   (long long)block, (long long)h->last_first_block,
+                                                   (long long)(h->last_first_block + h->last_nblocks));
+    std::vector<uint8_t> bytes;
+    if (which == ERTGPU_TAP_SIGNAL || which == ERTGPU_TAP_CSUM) {
+        float* sig = h->d_tap;
+        float* cs = h->d_tap + (c.BS + c.SL);
+        tap_signal_csum_kernel<<<1, 32, 0, h->stream>>>(h->last_iq, h->last_hist, c.hist_samples, h->last_hist_valid, h->d_lut,
+                                                        b, c.BS, c.SL, sig, cs);
+        CUDA_TRY(h, cudaGetLastError());
+        const size_t n = which == ERTGPU_TAP_SIGNAL ? (size_t)(c.BS + c.SL) : (size_t)(c.BS + c.SL + 1);
+        bytes.resize(n * sizeof(float));
+        CUDA_TRY(h, cudaMemcpyAsync(bytes.data(), which == ERTGPU_TAP_SIGNAL ? sig : cs, bytes.size(), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    } else if (which == ERTGPU_TAP_QUANTIZED || which == ERTGPU_TAP_PACKED) {
+        // Quantized after block b = stream bits [(b+1)*BS - BUF, (b+1)*BS)  (decode.go:166,172)
+        const long long first_bit = (long long)c.hist_words * 32 + (b + 1) * c.BS - c.BUF;
+        const long long w0 = first_bit >> 5, w1 = (first_bit + c.BUF + 31) >> 5;
+        std::vector<uint32_t> words((size_t)(w1 - w0));
+        CUDA_TRY(h, cudaMemcpy(words.data(), h->last_plane + w0, words.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        std::vector<uint8_t> q((size_t)c.BUF);
+        for (long long i = 0; i < c.BUF; i++) {
+            const long long pos = first_bit + i - (w0 << 5);
+            q[(size_t)i] = (uint8_t)((words[(size_t)(pos >> 5)] >> (31 - (pos & 31))) & 1u);
+        }
+        if (which == ERTGPU_TAP_QUANTIZED) {
+            bytes = q;
+        } else {  // decode.go:259-265
+            bytes.resize((size_t)((c.BS + c.PL + 7) >> 3));
+            for (size_t B = 0; B < bytes.size(); B++) {
+                uint8_t v = 0;
+                for (int k = 0; k < 8; k++) v = (uint8_t)((v << 1) | q[B * 8 + k]);
+                bytes[B] = v;
+            }
+        }
+    } else if (which == ERTGPU_TAP_R900_QUANTIZED) {
+        float* cs = h->d_tap;
+        uint8_t* qd = reinterpret_cast<uint8_t*>(h->d_tap + c.BUF + 4);
+        tap_r900_csum_kernel<<<1, 32, 0, h->stream>>>(h->last_iq, h->last_hist, c.hist_samples, h->last_hist_valid, h->d_lut, b,
+                                                      c.BS, c.BUF, cs);
+        CUDA_TRY(h, cudaGetLastError());
+        tap_r900_digits_kernel<<<(c.BUF + 255) / 256, 256, 0, h->stream>>>(cs, c.BUF, c.CL, qd);
+        CUDA_TRY(h, cudaGetLastError());
+        bytes.resize((size_t)c.BUF);
+        CUDA_TRY(h, cudaMemcpyAsync(bytes.data(), qd, bytes.size(), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    } else {
+        return fail(h, ERTGPU_EINVAL, "unknown tap %d", which);
+    }
+    if (n_out) *n_out = bytes.size();
+    if (dst) memcpy(dst, bytes.data(), std::min(cap, bytes.size()));
+    return ERTGPU_OK;
+}
+
+int ertgpu_host_alloc(void** out, size_t nbytes) {
+    if (!out) return ERTGPU_EINVAL;
+    cudaError_t e = cudaHostAlloc(out, nbytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? ERTGPU_ENOMEM : ERTGPU_ECUDA;
+    }
+    return ERTGPU_OK;
+}
+
+int ertgpu_host_free(void* p) {
+    if (!p) return ERTGPU_OK;
+    return cudaFreeHost(p) == cudaSuccess ? ERTGPU_OK : ERTGPU_ECUDA;
+}
+
+int ertgpu_synth_fill(int32_t device, void* d_out, int64_t first_sample, int64_t nsamples, uint64_t seed,
+                      const ertgpu_synth_packet* packets, int64_t npackets, void* stream) {
+    if (!d_out || nsamples < 0 || npackets < 0 || (npackets && !packets)) return ERTGPU_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return ERTGPU_ECUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    ertgpu_synth_packet* d_pk = nullptr;
+    // only the packets that can touch [first_sample, first_sample + nsamples) are uploaded
+    int64_t lo = 0, hi = npackets;
+    while (lo < npackets && packets[lo].start_sample + (int64_t)packets[lo].n_chips * packets[lo].chip_length <= first_sample) lo++;
+    while (hi > lo && packets[hi - 1].start_sample >= first_sample + nsamples) hi--;
+    const int64_t n = hi - lo;
+    if (cudaMalloc(&d_pk, std::max<int64_t>(n, 1) * sizeof(ertgpu_synth_packet)) != cudaSuccess) return ERTGPU_ENOMEM;
+    if (n && cudaMemcpyAsync(d_pk, packets + lo, (size_t)n * sizeof(ertgpu_synth_packet), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        cudaFree(d_pk);
+        return ERTGPU_ECUDA;
+    }
+    long long groups = (nsamples + 7) / 8;
+    long long blocks = std::min<long long>((groups + 255) / 256, 148 * 32);
+    if (blocks < 1) blocks = 1;
+    synth_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<uint8_t*>(d_out), first_sample, nsamples, seed, d_pk, n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_pk);
+    return e == cudaSuccess ? ERTGPU_OK : ERTGPU_ECUDA;
+}
+
+}  // extern "C"

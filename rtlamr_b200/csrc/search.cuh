@@ -1,0 +1,214 @@
+// search.cuh -- preamble Search, Slice and the per-candidate integrity screens on the packed
+// bit-plane produced by the demod kernels.
+//
+// Replaces Decoder.Search (protocol/decode.go:255-328), Decoder.Slice (decode.go:353-375) and
+// the CRC calls each parser makes on every candidate (scm/scm.go:76, scmplus/scmplus.go:77,
+// idm/idm.go:77-87, netidm/netidm.go:88-98; crc/crc.go:49-55), plus the DSP half of
+// r900.Parser.Parse for the candidates it inspects (r900/r900.go:160-207).
+//
+// Search semantics: the reference's byte pre-filter (decode.go:268-294) is only a CPU
+// shortcut; for every legal chip length (SL % 8 == 0) its net result is "every idx in
+// [0, BlockSize) whose bits at idx + k*SL equal the preamble" (SURVEY.md section 2.1 step 5).
+// The kernel computes exactly that set, 32 start positions at a time: the hit mask of a word
+// of starts is the AND over the preamble bits k of (plane window at +k*SL) XNOR P[k].
+#pragma once
+
+#include "demod_generic.cuh"
+#include "ert_common.cuh"
+
+namespace ert {
+
+// grid-stride over words of start positions.  plane bit index of start s is p0 + s.
+__global__ void search_kernel(const uint32_t* __restrict__ plane, long long p0, long long nwords,
+                              DevCfg cfg, RawHit* __restrict__ hits, unsigned long long hit_cap,
+                              unsigned long long* __restrict__ hit_count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride) {
+        const long long base = p0 + (w << 5);
+        for (int p = 0; p < cfg.npre; p++) {
+            uint32_t m = 0xFFFFFFFFu;
+            const int nb = cfg.pre_nbits[p];
+            for (int k = 0; k < nb && m; k++) {
+                const uint32_t x = plane_window(plane, base + (long long)k * cfg.SL);
+                m &= cfg.pre_bits[p][k] ? x : ~x;
+            }
+            while (m) {
+                const int lead = __clz(m);  // MSB = first start of the word
+                m &= ~(0x80000000u >> lead);
+                const unsigned long long slot = atomicAdd(hit_count, 1ull);
+                if (slot < hit_cap) {
+                    RawHit h;
+                    h.s = (unsigned long long)((w << 5) + lead);
+                    h.preamble_id = p;
+                    h.pad = 0;
+                    hits[slot] = h;
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint16_t crc16(const uint16_t* __restrict__ tbl, uint16_t init,
+                                          const uint8_t* data, int n) {
+    uint16_t crc = init;
+    for (int i = 0; i < n; i++) crc = (uint16_t)((crc << 8) ^ tbl[(crc >> 8) ^ data[i]]);  // crc.go:52-54
+    return crc;
+}
+
+// GF(32) log/exp for the r900 syndrome screen (r900/gf/gf.go:20-57 with order 32, poly 37, generator 2)
+struct Gf32 {
+    uint8_t exp[62];
+    uint8_t log[32];
+};
+
+__device__ __forceinline__ uint8_t gf_mul(const Gf32& g, uint8_t x, uint8_t y) {
+    if (x == 0 || y == 0) return 0;
+    return g.exp[g.log[x] + g.log[y]];
+}
+
+// One CTA per candidate (grid-stride).  Thread j < packet_bytes gathers byte j of the packet
+// (8 strided plane bits, decode.go:363-366); thread 0 then runs the screens of every parser
+// registered under the candidate's preamble.
+// If `r900_digits` is non-null it holds, per raw hit, the 42 payload digits computed by
+// r900_replay_kernel.
+__global__ void extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg,
+                               const RawHit* __restrict__ hits, unsigned long long hit_cap,
+                               const unsigned long long* __restrict__ hit_count,
+                               const uint16_t* __restrict__ crc_tables, Gf32 gf,
+                               const uint8_t* __restrict__ r900_digits, long long first_block,
+                               uint32_t flags, ertgpu_candidate* __restrict__ out,
+                               unsigned long long out_cap, unsigned long long* __restrict__ out_count,
+                               unsigned long long* __restrict__ valid_count) {
+    __shared__ uint8_t bytes[ERTGPU_MAX_PACKET_BYTES + 4];
+    unsigned long long n = *hit_count;
+    if (n > hit_cap) n = hit_cap;
+    for (unsigned long long c = blockIdx.x; c < n; c += gridDim.x) {
+        const RawHit h = hits[c];
+        const int j = threadIdx.x;
+        if (j < ERTGPU_MAX_PACKET_BYTES) {
+            uint32_t v = 0;
+            if (j < cfg.packet_bytes) {
+                for (int k = 0; k < 8; k++) {
+                    const int sym = j * 8 + k;
+                    uint32_t bit = 0;
+                    if (sym < cfg.PK) bit = plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL);
+                    v = (v << 1) | bit;
+                }
+            }
+            bytes[j] = (uint8_t)v;
+        }
+        __syncthreads();
+        if (j == 0) {
+            uint32_t mask = 0;
+            const uint8_t* dig = r900_digits ? r900_digits + c * ERTGPU_R900_DIGITS : nullptr;
+            for (int i = 0; i < cfg.nproto; i++) {
+                const DevProto& pr = cfg.proto[i];
+                if (pr.preamble_id != h.preamble_id) continue;
+                bool ok = false;
+                const uint16_t* tbl = crc_tables + 256 * pr.table;
+                if (pr.check_kind == ERTGPU_CHECK_NONE) {
+                    ok = true;
+                } else if (pr.check_kind == ERTGPU_CHECK_CRC16) {
+                    ok = crc16(tbl, pr.crc_init, bytes + pr.crc_from, pr.crc_to - pr.crc_from) == pr.crc_residue;
+                } else if (pr.check_kind == ERTGPU_CHECK_IDM) {
+                    ok = crc16(tbl, pr.crc_init, bytes + 4, 88) == pr.crc_residue;  // idm.go:77
+                    if (ok) {
+                        uint8_t buf[6] = {bytes[9], bytes[10], bytes[11], bytes[12], bytes[88], bytes[89]};
+                        ok = crc16(tbl, pr.crc_init, buf, 6) == pr.crc_residue;     // idm.go:82-87
+                    }
+                } else if (pr.check_kind == ERTGPU_CHECK_R900 && dig) {
+                    uint8_t msg[31];
+                    for (int q = 0; q < 31; q++) msg[q] = 0;
+                    ok = true;
+                    for (int q = 0; q < 21 && ok; q++) {            // r900.go:199-207
+                        const int sym = dig[2 * q] * 6 + dig[2 * q + 1];
+                        if (sym > 31) ok = false;
+                        msg[q < 16 ? q : q + 10] = (uint8_t)sym;    // r900.go:215-216
+                    }
+                    for (int s = 0; s < 5 && ok; s++) {             // gf.go:163-169, Syndrome(msg,5,29)
+                        const uint8_t root = gf.exp[(29 + s) % 31];
+                        uint8_t syn = msg[0];
+                        for (int q = 1; q < 31; q++) syn = gf_mul(gf, syn, root) ^ msg[q];
+                        if (syn) ok = false;
+                    }
+                }
+                if (ok) mask |= 1u << i;
+            }
+            if (mask) atomicAdd(valid_count, 1ull);
+            if (mask || !(flags & ERTGPU_DECODE_ONLY_VALID)) {
+                const unsigned long long slot = atomicAdd(out_count, 1ull);
+                if (slot < out_cap) {
+                    ertgpu_candidate* o = out + slot;
+                    o->block = first_block + (long long)(h.s / (unsigned long long)cfg.BS);
+                    o->idx = (int32_t)(h.s % (unsigned long long)cfg.BS);
+                    o->preamble_id = h.preamble_id;
+                    o->check_mask = mask;
+                    o->flags = dig && cfg.pre_has_r900[h.preamble_id] ? ERTGPU_CAND_HAS_R900 : 0u;
+                    for (int q = 0; q < ERTGPU_MAX_PACKET_BYTES; q++) o->bytes[q] = bytes[q];
+                    for (int q = 0; q < ERTGPU_R900_DIGITS; q++)
+                        o->r900_digits[q] = (dig && cfg.pre_has_r900[h.preamble_id]) ? dig[q] : 0;
+                    o->pad[0] = o->pad[1] = 0;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// r900 payload digits for each raw hit of an r900 preamble: exact replay of the parser's own
+// running sum (r900/r900.go:96-100), which restarts at sample (b+1)*BS - BUF of the block b
+// that detects the candidate, up to the last payload correlator window.  One thread per hit;
+// only the 169 running-sum values at payload + t*CL (t = 0..168) are kept.
+__global__ void r900_replay_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist,
+                                   int hist_samples, int hist_valid, const float* __restrict__ lut_g,
+                                   DevCfg cfg, const RawHit* __restrict__ hits, unsigned long long hit_cap,
+                                   const unsigned long long* __restrict__ hit_count,
+                                   uint8_t* __restrict__ digits) {
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
+    __syncthreads();
+    unsigned long long n = *hit_count;
+    if (n > hit_cap) n = hit_cap;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+        const RawHit h = hits[c];
+        if (!cfg.pre_has_r900[h.preamble_id]) continue;
+        const long long b = (long long)(h.s / (unsigned long long)cfg.BS);
+        const int idx = (int)(h.s % (unsigned long long)cfg.BS);
+        const long long first = (b + 1) * cfg.BS - cfg.BUF;  // sample of r900 signal[0]
+        const int payload = idx + cfg.PL - cfg.SL;           // r900.go:187
+        const int last = payload + 4 * ERTGPU_R900_DIGITS * cfg.CL;  // csum index of the final tap
+        float taps[4 * ERTGPU_R900_DIGITS + 1];
+        float s = 0.0f;
+        int next = payload, ti = 0;
+        if (next == 0) { taps[ti++] = 0.0f; next += cfg.CL; }
+        for (int t = 0; t < last; t++) {
+            s = __fadd_rn(s, mag_at(iq, hist, hist_samples, hist_valid, first + t, lut));
+            if (t + 1 == next) { taps[ti++] = s; next += cfg.CL; }
+        }
+        uint8_t* d = digits + c * ERTGPU_R900_DIGITS;
+        for (int k = 0; k < ERTGPU_R900_DIGITS; k++)
+            d[k] = r900_digit(taps[4 * k], taps[4 * k + 1], taps[4 * k + 2], taps[4 * k + 3], taps[4 * k + 4]);
+    }
+}
+
+// Carry the last `hist_words` words of a call's plane to the front of the other plane, and the
+// last `hist_samples` IQ samples into the other history buffer (ping-pong: no overlap hazards).
+__global__ void carry_kernel(const uint32_t* __restrict__ plane_src, uint32_t* __restrict__ plane_dst,
+                             long long src_offset_words, int hist_words,
+                             const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_src,
+                             uint8_t* __restrict__ hist_dst, int hist_samples, long long nsamples) {
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = i0; i < hist_words; i += stride) plane_dst[i] = plane_src[src_offset_words + i];
+    // hist_dst[k] (k in [0,hist_samples)) = sample (nsamples - hist_samples + k) relative to the call
+    for (int k = i0; k < hist_samples; k += stride) {
+        const long long j = nsamples - hist_samples + k;
+        uint16_t v;
+        if (j >= 0) v = reinterpret_cast<const uint16_t*>(iq)[j];
+        else v = reinterpret_cast<const uint16_t*>(hist_src)[hist_samples + j];
+        reinterpret_cast<uint16_t*>(hist_dst)[k] = v;
+    }
+}
+
+}  // namespace ert
