@@ -94,7 +94,7 @@ typedef struct {
     int32_t preamble_id;  /* distinct preamble, in registration order              */
     uint32_t check_mask;  /* bit i: i-th registered protocol passed its screen     */
     uint32_t flags;       /* ERTGPU_CAND_*                                         */
-    uint8_t bytes[ERTGPU_MAX_PACKET_BYTES]; /* Data.Bytes (merged PacketSymbols, MSB first; pad bits 0) */
+    uint8_t bytes[ERTGPU_MAX_PACKET_BYTES]; /* Data.Bytes (merged PacketSymbols, MSB first; a trailing partial byte holds its PK%8 bits in the low bits, like decode.go:363-366 on a zeroed pkt) */
     uint8_t r900_digits[ERTGPU_R900_DIGITS]; /* r900 quantized[] at the 42 payload positions, r900/r900.go:187-193 */
     uint8_t pad[2];
 } ertgpu_candidate;

@@ -44,9 +44,9 @@ __global__ void demod_generic_kernel(const uint8_t* __restrict__ iq, const uint8
                                      int hist_samples, int hist_valid, const float* __restrict__ lut_g,
                                      uint32_t* __restrict__ plane_out,  // word 0 = first bit of block 0 of the call
                                      long long nblocks, int BS, int CL) {
-    extern __shared__ float smem[];
-    float* lut = smem;                         // 256
-    float* cring = smem + 256;                 // [CL][blockDim.x]
+    extern __shared__ float gen_smem[];
+    float* lut = gen_smem;                       // 256
+    float* cring = gen_smem + 256;                 // [CL][blockDim.x]
     float* aring = cring + CL * blockDim.x;    // [CL][blockDim.x]
     const int tid = threadIdx.x, nthr = blockDim.x;
     for (int i = tid; i < 256; i += nthr) lut[i] = lut_g[i];

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -55,7 +56,7 @@ struct ertgpu_handle {
     uint8_t* d_digits = nullptr;
     ertgpu_candidate* d_out = nullptr;
     unsigned long long cand_cap = 0;
-    unsigned long long* d_counters = nullptr;  // [0]=hits [1]=out [2]=valid
+    unsigned long long* d_counters = nullptr;  // [0]=hits [1]=out [2]=valid [3]=demod work-tile counter
     unsigned long long* h_counters = nullptr;  // pinned mirror
     float* d_tap = nullptr;                    // scratch for taps
     size_t tap_floats = 0;
@@ -64,6 +65,7 @@ struct ertgpu_handle {
     int64_t block_counter = 0;  // number of reference Decode calls consumed so far
     bool has_r900 = false;
     int demod_variant = 0;      // 0 generic, else specialised chip length
+    int demod_warps = 0;        // 0 default; tuning override (env ERTGPU_FAST_WARPS)
 
     // state of the last enqueued pipeline (for fetch and taps)
     bool pending = false;
@@ -176,12 +178,12 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     const long long p0 = (long long)c.hist_words * 32 - c.PKL;
     h->launches = 0;
 
-    CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, 3 * sizeof(unsigned long long), st));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
 
     // 1. magnitude + matched filter + quantize + pack
     if (h->demod_variant != 0) {
-        int rc = launch_demod_fast(h->demod_variant, d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut,
-                                   plane + c.hist_words, nblocks, c.BS, st);
+        int rc = launch_demod_fast(h->demod_variant, h->demod_warps, d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut,
+                                   plane + c.hist_words, nblocks, c.BS, h->d_counters + 3, st);
         if (rc != 0) return fail(h, ERTGPU_ECUDA, "demod_fast launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     } else {
         int nthr = 128;
@@ -489,6 +491,7 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
     CUDA_TRY(h, cudaMalloc(&h->d_tap, h->tap_floats * sizeof(float)));
 
     h->demod_variant = demod_fast_variant(d.CL, d.BS);
+    if (const char* e = getenv("ERTGPU_FAST_WARPS")) h->demod_warps = atoi(e);
     h->cur_plane = h->cur_hist = 0;
     h->hist_valid = 0;
     h->block_counter = 0;

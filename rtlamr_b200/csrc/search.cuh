@@ -90,9 +90,8 @@ __global__ void extract_kernel(const uint32_t* __restrict__ plane, long long p0,
             if (j < cfg.packet_bytes) {
                 for (int k = 0; k < 8; k++) {
                     const int sym = j * 8 + k;
-                    uint32_t bit = 0;
-                    if (sym < cfg.PK) bit = plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL);
-                    v = (v << 1) | bit;
+                    // a trailing partial byte is filled like a fresh d.pkt: PK%8 shifts only (decode.go:363-366)
+                    if (sym < cfg.PK) v = (v << 1) | plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL);
                 }
             }
             bytes[j] = (uint8_t)v;
