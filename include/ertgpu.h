@@ -179,6 +179,13 @@ int ertgpu_last_counts(ertgpu_handle *h, int64_t *n_candidates, int64_t *n_valid
 /* Kernels launched by the last decode call (for bench.py's gpu_launches). */
 int64_t ertgpu_last_launches(const ertgpu_handle *h);
 
+/* Per-stage device timing of the decode pipeline (CUDA events recorded on the
+ * launching stream around each stage; for bench.py's roofline).  After a decode
+ * with timing enabled, ms4[] = {demod (magnitude+filter+quantize+pack),
+ * search, slice+screens (+r900 replay), history carry} of the last pipeline. */
+int ertgpu_set_stage_timing(ertgpu_handle *h, int32_t enable);
+int ertgpu_last_stage_ms(ertgpu_handle *h, float *ms4);
+
 /* Parity tap: reference buffer `which` as it would be after the Decode of
  * block `block` (absolute index; must lie inside the last decode call).
  * Writes up to cap bytes to dst (host), *n_out = bytes of the full tap. */

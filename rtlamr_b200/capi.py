@@ -63,7 +63,8 @@ EXPORTS = [
     "ertgpu_abi_version", "ertgpu_last_error", "ertgpu_create", "ertgpu_destroy",
     "ertgpu_register_protocol", "ertgpu_stock_protocol", "ertgpu_allocate", "ertgpu_get_config",
     "ertgpu_reset", "ertgpu_decode", "ertgpu_decode_device_async", "ertgpu_fetch",
-    "ertgpu_last_counts", "ertgpu_last_launches", "ertgpu_tap", "ertgpu_set_demod_variant",
+    "ertgpu_last_counts", "ertgpu_last_launches", "ertgpu_set_stage_timing",
+    "ertgpu_last_stage_ms", "ertgpu_tap", "ertgpu_set_demod_variant",
     "ertgpu_host_alloc", "ertgpu_host_free", "ertgpu_synth_fill",
 ]
 
@@ -105,6 +106,8 @@ def lib() -> C.CDLL:
     L.ertgpu_last_launches.restype = i64
     L.ertgpu_last_launches.argtypes = [vp]
     L.ertgpu_tap.argtypes = [vp, i32, i64, vp, sz, C.POINTER(sz)]
+    L.ertgpu_set_stage_timing.argtypes = [vp, i32]
+    L.ertgpu_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.ertgpu_set_demod_variant.argtypes = [vp, i32]
     L.ertgpu_host_alloc.argtypes = [C.POINTER(vp), sz]
     L.ertgpu_host_free.argtypes = [vp]
@@ -199,6 +202,14 @@ class Handle:
 
     def last_launches(self) -> int:
         return int(self._L.ertgpu_last_launches(self._h))
+
+    def set_stage_timing(self, enable: bool):
+        self._check(self._L.ertgpu_set_stage_timing(self._h, 1 if enable else 0))
+
+    def last_stage_ms(self):
+        ms = (C.c_float * 4)()
+        self._check(self._L.ertgpu_last_stage_ms(self._h, ms))
+        return dict(zip(("demod", "search", "extract", "carry"), [float(x) for x in ms]))
 
     def tap(self, which: int, block: int) -> np.ndarray:
         n = C.c_size_t(0)

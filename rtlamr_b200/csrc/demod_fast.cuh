@@ -25,6 +25,8 @@
 //    per-block bit-plane row.
 #pragma once
 
+#include <cuda.h>
+
 #include "ert_common.cuh"
 
 namespace ert {
@@ -57,6 +59,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// 2D tiled TMA load: box (x = byte column, y = block row) -> dense smem tile
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -87,9 +96,10 @@ struct FastGeom {
 //   [staging of the remaining warps ...]
 template <int CL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
-demod_fast_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist, int hist_samples,
-                  int hist_valid, const float* __restrict__ lut_g, uint32_t* __restrict__ plane_out,
-                  long long nblocks, int BS, unsigned long long* __restrict__ tile_counter) {
+demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __restrict__ iq,
+                  const uint8_t* __restrict__ hist, int hist_samples, int hist_valid,
+                  const float* __restrict__ lut_g, uint32_t* __restrict__ plane_out, long long nblocks, int BS,
+                  unsigned long long* __restrict__ tile_counter) {
     using G = FastGeom<CL>;
     extern __shared__ __align__(128) uint8_t fast_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -109,8 +119,8 @@ demod_fast_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hi
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_base + v * 256 + l * 4), "f"(x) : "memory");
     }
     if (lane == 0) {
-        mbar_init(bar0, 32);
-        mbar_init(bar0 + 8, 32);
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -141,16 +151,33 @@ demod_fast_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hi
         const uint32_t blk16 = (uint32_t)((b * 2ll * BS) >> 4);  // block start in 16-byte units
         const bool first = (b == 0);
         const uint32_t lo_lead = (first && !have_hist) ? (lut_base | 128u) : lo_main;
+        // Body t of the 32 chains of this work tile = one [32 rows][2*CL bytes] box of the IQ
+        // matrix (row = reference block, BlockSize2 bytes per row): a single TMA tile load issued
+        // by one lane.  Rows past the end of the call and columns past the end of a row are
+        // zero-filled by the TMA unit (the steps that read them produce no output).
+        // The first work tile of a call is the exception: block 0 takes its lead-in from the
+        // history buffer, so that tile uses one 1D bulk copy per lane instead.
+        const bool lane_copies = (tile == 0);
         auto issue = [&](int t) {
             if (t >= nbody) return;
+            const uint32_t bar = bar0 + (t & 1) * 8;
+            if (!lane_copies) {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(bar, 32u * G::kStrideBytes);
+                    const int x = (t < 2) ? 2 * BS - 2 * G::kRowBytes + t * G::kRowBytes : (t - 2) * G::kRowBytes;
+                    const int y = (int)(tile * 32) - (t < 2 ? 1 : 0);
+                    tma_load_2d(stage0 + (t & 1) * G::kStageBytes, &iq_map, x, y, bar);
+                }
+                return;
+            }
             const int off16 = t * G::kRowUnits;
             int n16 = chain_units - off16;
             if (n16 > G::kRowUnits) n16 = G::kRowUnits;
             const uint8_t* src;
             if (t < 2 && first) src = have_hist ? hist_lead + 16ll * off16 : iq;
             else src = iq + 16ll * ((long long)blk16 + off16 - 2 * G::kRowUnits);
-            const uint32_t bar = bar0 + (t & 1) * 8;
-            mbar_arrive_expect_tx(bar, (uint32_t)n16 * 16u);
+            if (lane == 0) mbar_arrive_expect_tx(bar, 32u * (uint32_t)n16 * 16u);
+            __syncwarp();
             bulk_g2s(row + (t & 1) * G::kStageBytes, src, (uint32_t)n16 * 16u, bar);
         };
         issue(0);
@@ -204,7 +231,8 @@ demod_fast_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hi
                     }
                 }
             }
-            // everything read from this stage is in registers: refill it with body t+2
+            // every lane has read its row of this stage into registers: refill it with body t+2
+            __syncwarp();
             issue(t + 2);
 
             if constexpr (G::kTailBits != 0) {
@@ -238,10 +266,27 @@ constexpr int fast_warps() {
     return (2 * CL + 40 <= 128) ? 16 : ((2 * CL + 40 <= 168) ? 12 : 8);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
 template <int CL, int W>
 int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_samples, int hist_valid,
                          const float* lut, uint32_t* plane_out, long long nblocks, int BS,
                          unsigned long long* tile_counter, cudaStream_t st) {
+    using G = FastGeom<CL>;
     auto kern = demod_fast_kernel<CL, W>;
     const int smem = 227 * 1024;
     static bool configured = false;
@@ -250,6 +295,18 @@ int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_sample
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
+    // the IQ bytes of the call as a 2D uint8 tensor: [nblocks rows][BlockSize2 bytes]
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)(2 * BS), (cuuint64_t)nblocks};
+    const cuuint64_t gstride[1] = {(cuuint64_t)(2 * BS)};
+    const cuuint32_t box[2] = {(cuuint32_t)G::kStrideBytes, 32u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(iq), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
     const long long ntiles = (nblocks + 31) / 32;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -257,7 +314,7 @@ int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_sample
     long long grid = (ntiles + W - 1) / W;
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, W * 32, smem, st>>>(iq, hist, hist_samples, hist_valid, lut, plane_out, nblocks, BS, tile_counter);
+    kern<<<(unsigned)grid, W * 32, smem, st>>>(map, iq, hist, hist_samples, hist_valid, lut, plane_out, nblocks, BS, tile_counter);
     return (int)cudaGetLastError();
 }
 

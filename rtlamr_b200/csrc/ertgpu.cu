@@ -79,6 +79,9 @@ struct ertgpu_handle {
     unsigned long long need = 0;
     int64_t total_hits = 0, total_valid = 0;
     int64_t launches = 0;
+    bool stage_timing = false;
+    cudaEvent_t ev_stage[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool stage_valid = false;
     std::vector<ertgpu_candidate> results;
 };
 
@@ -153,6 +156,7 @@ void free_device(ertgpu_handle* h) {
         if (h->ev_h2d[k]) cudaEventDestroy(h->ev_h2d[k]);
         if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
     }
+    for (int k = 0; k < 5; k++) if (h->ev_stage[k]) cudaEventDestroy(h->ev_stage[k]);
     cudaFree(h->d_lut);
     cudaFree(h->d_crc);
     cudaFree(h->d_hits);
@@ -180,6 +184,8 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
 
     CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
 
+    const bool tm = h->stage_timing;
+    if (tm) CUDA_TRY(h, cudaEventRecord(h->ev_stage[0], st));
     // 1. magnitude + matched filter + quantize + pack
     if (h->demod_variant != 0) {
         int rc = launch_demod_fast(h->demod_variant, h->demod_warps, d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut,
@@ -197,6 +203,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
         CUDA_TRY(h, cudaGetLastError());
     }
     h->launches++;
+    if (tm) CUDA_TRY(h, cudaEventRecord(h->ev_stage[1], st));
 
     // 2. preamble search over every start position of the call
     {
@@ -209,6 +216,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
         h->launches++;
     }
 
+    if (tm) CUDA_TRY(h, cudaEventRecord(h->ev_stage[2], st));
     // 3. r900 payload digits for hits of an r900 preamble
     const uint8_t* digits = nullptr;
     if (h->has_r900) {
@@ -226,12 +234,15 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
 
+    if (tm) CUDA_TRY(h, cudaEventRecord(h->ev_stage[3], st));
     // 5. carry history to the other buffers
     carry_kernel<<<64, 256, 0, st>>>(plane, plane_next, nwords, c.hist_words, d_iq, hist, hist_next, c.hist_samples,
                                      nblocks * c.BS);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
 
+    if (tm) CUDA_TRY(h, cudaEventRecord(h->ev_stage[4], st));
+    h->stage_valid = tm;
     CUDA_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 
     h->last_iq = d_iq;
@@ -468,6 +479,7 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_h2d[k], cudaEventDisableTiming));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
     }
+    for (int k = 0; k < 5; k++) CUDA_TRY(h, cudaEventCreate(&h->ev_stage[k]));
     make_maglut(h->h_lut);
     make_gf32(&h->gf);
     CUDA_TRY(h, cudaMalloc(&h->d_lut, 256 * sizeof(float)));
@@ -681,6 +693,24 @@ int ertgpu_tap(ertgpu_handle* h, int32_t which, int64_t block, void* dst, size_t
     }
     if (n_out) *n_out = bytes.size();
     if (dst) memcpy(dst, bytes.data(), std::min(cap, bytes.size()));
+    return ERTGPU_OK;
+}
+
+int ertgpu_set_stage_timing(ertgpu_handle* h, int32_t enable) {
+    if (!h || !h->allocated) return ERTGPU_EINVAL;
+    h->stage_timing = enable != 0;
+    return ERTGPU_OK;
+}
+
+int ertgpu_last_stage_ms(ertgpu_handle* h, float* ms4) {
+    if (!h || !h->allocated || !ms4) return ERTGPU_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->pending) {
+        int rc = collect(h);
+        if (rc) return rc;
+    }
+    if (!h->stage_valid) return fail(h, ERTGPU_EINVAL, "stage timing was not enabled for the last decode");
+    for (int k = 0; k < 4; k++) CUDA_TRY(h, cudaEventElapsedTime(&ms4[k], h->ev_stage[k], h->ev_stage[k + 1]));
     return ERTGPU_OK;
 }
 
