@@ -210,13 +210,17 @@ def run_b200(args):
     torch.cuda.set_stream(stream)
     st = stream.cuda_stream
 
-    def step_device():
+    def step_device(fetch=False):
+        """One pass of the hot path over the resident batch: fresh stream, every kernel of the
+        pipeline, then the per-step result read-back (candidate / valid counters, D2H).  The
+        candidate records themselves are fetched when asked (correctness gate, e2e arm)."""
         h.reset()
         h.decode_device_async(d_iq.data_ptr(), nbytes, capi.DECODE_ONLY_VALID, st)
-        return h.fetch(1 << 17)
+        counts = h.last_counts()
+        return h.fetch(1 << 17) if fetch else counts
 
     # ---- correctness gate (untimed): every injected packet that lies in this rank's range decodes
-    got = step_device()
+    got = step_device(fetch=True)
     got = got[got["block"] >= (plan.first_block - plan.first_fed_block)]
     ids = {bytes(r["bytes"][:12]) for r in got}
     mine = [t for t in truth if plan.owns_start(t.start_sample + cfg.symbol_length, bs, cfg.buffer_length)

@@ -68,7 +68,10 @@ struct ertgpu_handle {
     int demod_warps = 0;        // 0 default; tuning override (env ERTGPU_FAST_WARPS)
 
     // state of the last enqueued pipeline (for fetch and taps)
-    bool pending = false;
+    bool pending = false;       // a pipeline is enqueued and not yet synchronised
+    bool uncopied = false;      // ... synchronised, candidates still only on the device
+    unsigned long long uncopied_n = 0;
+    bool fresh = true;          // next pipeline must see zeroed history (start of stream / after reset)
     cudaStream_t pending_stream = nullptr;
     const uint8_t* last_iq = nullptr;
     const uint8_t* last_hist = nullptr;
@@ -183,6 +186,10 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     h->launches = 0;
 
     CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    if (h->fresh) {  // Quantized starts as zeros (decode.go:145); only the history in front of the call is read
+        CUDA_TRY(h, cudaMemsetAsync(plane, 0, (size_t)c.hist_words * sizeof(uint32_t), st));
+        h->fresh = false;
+    }
 
     const bool tm = h->stage_timing;
     if (tm) CUDA_TRY(h, cudaEventRecord(h->ev_stage[0], st));
@@ -262,8 +269,8 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     return ERTGPU_OK;
 }
 
-// Wait for the pending pipeline and append its candidates to h->results.
-int collect(ertgpu_handle* h) {
+// Wait for the pending pipeline and read its counters (candidates stay on the device).
+int collect_sync(ertgpu_handle* h) {
     if (!h->pending) return ERTGPU_OK;
     CUDA_TRY(h, cudaStreamSynchronize(h->pending_stream));
     h->pending = false;
@@ -274,11 +281,20 @@ int collect(ertgpu_handle* h) {
         h->overflow = true;
         h->need = std::max(h->need, nh);
     }
-    const unsigned long long take = std::min(no, h->cand_cap);
-    if (take) {
+    h->uncopied_n = std::min(no, h->cand_cap);
+    h->uncopied = h->uncopied_n > 0;
+    return ERTGPU_OK;
+}
+
+// ... and append its candidates to h->results.
+int collect(ertgpu_handle* h) {
+    int rc = collect_sync(h);
+    if (rc) return rc;
+    if (h->uncopied) {
         const size_t old = h->results.size();
-        h->results.resize(old + take);
-        CUDA_TRY(h, cudaMemcpy(h->results.data() + old, h->d_out, take * sizeof(ertgpu_candidate), cudaMemcpyDeviceToHost));
+        h->results.resize(old + h->uncopied_n);
+        CUDA_TRY(h, cudaMemcpy(h->results.data() + old, h->d_out, h->uncopied_n * sizeof(ertgpu_candidate), cudaMemcpyDeviceToHost));
+        h->uncopied = false;
     }
     return ERTGPU_OK;
 }
@@ -304,6 +320,7 @@ int deliver(ertgpu_handle* h, ertgpu_candidate* out, size_t cap, size_t* n_out) 
 
 void begin_call(ertgpu_handle* h) {
     h->results.clear();
+    h->uncopied = false;
     h->overflow = false;
     h->need = 0;
     h->total_hits = h->total_valid = 0;
@@ -524,10 +541,9 @@ int ertgpu_reset(ertgpu_handle* h) {
         CUDA_TRY(h, cudaStreamSynchronize(h->pending_stream));
         h->pending = false;
     }
-    // only the history in front of the next call has to read as zeros (decode.go:144-145)
-    for (int k = 0; k < 2; k++)
-        CUDA_TRY(h, cudaMemsetAsync(h->d_plane[k], 0, (size_t)h->dcfg.hist_words * sizeof(uint32_t), h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->uncopied = false;
+    // the history in front of the next call is zeroed on that call's stream (enqueue_pipeline)
+    h->fresh = true;
     h->hist_valid = 0;
     h->block_counter = 0;
     begin_call(h);
@@ -622,7 +638,7 @@ int ertgpu_last_counts(ertgpu_handle* h, int64_t* n_candidates, int64_t* n_valid
     if (!h || !h->allocated) return ERTGPU_EINVAL;
     if (h->pending) {
         CUDA_TRY(h, cudaSetDevice(h->device));
-        int rc = collect(h);
+        int rc = collect_sync(h);  // counters only; ertgpu_fetch copies the candidates if wanted
         if (rc) return rc;
     }
     if (n_candidates) *n_candidates = h->total_hits;
@@ -706,7 +722,7 @@ int ertgpu_last_stage_ms(ertgpu_handle* h, float* ms4) {
     if (!h || !h->allocated || !ms4) return ERTGPU_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (h->pending) {
-        int rc = collect(h);
+        int rc = collect_sync(h);
         if (rc) return rc;
     }
     if (!h->stage_valid) return fail(h, ERTGPU_EINVAL, "stage timing was not enabled for the last decode");
