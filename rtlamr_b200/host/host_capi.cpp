@@ -1,0 +1,111 @@
+// host_capi.cpp -- a small C surface over the C++ protocol mirror so that the Python parity tests
+// (and a CLI) can drive Decoder/Parser exactly like rtlamr's main.go does (main.go:59-86,235).
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+#include "protocol.hpp"
+
+extern "C" {
+
+struct erthost_msg {
+    int64_t block;
+    int32_t idx;
+    uint32_t meter_id;
+    uint32_t meter_type;
+    int32_t nchecksum;
+    uint8_t checksum[8];
+    char msgtype[12];
+    char text[1400];    // Message.String()
+    char record[1400];  // Message.Record() joined with ','
+};
+
+struct erthost {
+    protocol::Decoder d;
+    std::string err;
+};
+
+// main.go:59-86: NewDecoder; for each -msgtype NewParser + RegisterProtocol; Allocate
+erthost* erthost_new(const char* msgtypes_csv, int chip_length, int device, long long max_blocks, long long max_cands,
+                     char* errbuf, int errcap) {
+    try {
+        protocol::RegisterStockParsers();
+        auto* h = new erthost();
+        std::stringstream ss(msgtypes_csv);
+        std::string name;
+        while (std::getline(ss, name, ',')) {
+            if (name.empty()) continue;
+            h->d.RegisterProtocol(protocol::NewParser(name, chip_length));
+        }
+        h->d.Allocate(device, max_blocks, max_cands);
+        return h;
+    } catch (const std::exception& e) {
+        if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", e.what());
+        return nullptr;
+    }
+}
+
+void erthost_free(erthost* h) { delete h; }
+
+const char* erthost_error(const erthost* h) { return h ? h->err.c_str() : ""; }
+
+int erthost_config(const erthost* h, int32_t* out12) {
+    const protocol::PacketConfig& c = h->d.Cfg;
+    const int32_t v[12] = {c.DataRate, c.BlockSize, c.BlockSize2, c.ChipLength, c.SymbolLength, c.SampleRate,
+                           c.PreambleSymbols, c.PacketSymbols, c.PreambleLength, c.PacketLength, c.BufferLength,
+                           (int32_t)c.CenterFreq};
+    memcpy(out12, v, sizeof(v));
+    return 0;
+}
+
+int erthost_reset(erthost* h) {
+    try {
+        h->d.Reset();
+        return 0;
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return -1;
+    }
+}
+
+// rcvr.d.Decode(block) for N blocks (main.go:235); returns the number of messages (all are counted,
+// the first `cap` are written), or -1 on error / -2 when len is not a multiple of BlockSize2.
+long long erthost_decode(erthost* h, const uint8_t* iq, size_t len, erthost_msg* out, long long cap) {
+    try {
+        auto msgs = h->d.Decode(iq, len);
+        long long n = 0;
+        for (auto& m : msgs) {
+            if (n < cap) {
+                erthost_msg& o = out[n];
+                memset(&o, 0, sizeof(o));
+                o.block = m->Block;
+                o.idx = m->Idx;
+                o.meter_id = m->MeterID();
+                o.meter_type = m->MeterType();
+                auto ck = m->Checksum();
+                o.nchecksum = (int32_t)ck.size();
+                memcpy(o.checksum, ck.data(), std::min<size_t>(ck.size(), 8));
+                snprintf(o.msgtype, sizeof(o.msgtype), "%s", m->MsgType().c_str());
+                snprintf(o.text, sizeof(o.text), "%s", m->String().c_str());
+                std::string rec;
+                for (auto& f : m->Record()) rec += (rec.empty() ? "" : ",") + f;
+                snprintf(o.record, sizeof(o.record), "%s", rec.c_str());
+            }
+            n++;
+        }
+        return n;
+    } catch (const std::length_error& e) {
+        h->err = e.what();
+        return -2;
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return -1;
+    }
+}
+
+int erthost_log(const erthost* h, char* buf, int cap) {
+    snprintf(buf, (size_t)cap, "%s", h->d.Log().c_str());
+    return 0;
+}
+
+}  // extern "C"
