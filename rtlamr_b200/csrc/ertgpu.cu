@@ -235,7 +235,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     }
 
     // 4. slice + integrity screens
-    extract_kernel<<<148 * 4, 96, 0, st>>>(plane, p0, c, h->d_hits, h->cand_cap, h->d_counters, h->d_crc, h->gf,
+    extract_kernel<<<148 * 8, kExtractWarps * 32, 0, st>>>(plane, p0, c, h->d_hits, h->cand_cap, h->d_counters, h->d_crc, h->gf,
                                            digits, h->block_counter, flags, h->d_out, h->cand_cap,
                                            h->d_counters + 1, h->d_counters + 2);
     CUDA_TRY(h, cudaGetLastError());

@@ -18,18 +18,38 @@
 
 namespace ert {
 
-// grid-stride over words of start positions.  plane bit index of start s is p0 + s.
-__global__ void search_kernel(const uint32_t* __restrict__ plane, long long p0, long long nwords,
-                              DevCfg cfg, RawHit* __restrict__ hits, unsigned long long hit_cap,
-                              unsigned long long* __restrict__ hit_count) {
+// 32 consecutive plane bits starting at bit `pos` (first bit in the MSB), branch free
+__device__ __forceinline__ uint32_t plane_window2(const uint32_t* __restrict__ plane, long long pos) {
+    const long long w = pos >> 5;
+    return __funnelshift_l(plane[w + 1], plane[w], (int)(pos & 31));
+}
+
+// grid-stride over words of 32 start positions; plane bit index of start s is p0 + s.
+// Two phases per preamble: the first kSearchProbe preamble bits are tested unconditionally
+// (straight-line code, no divergence: 1/256 of the starts survive on noise), the remaining bits
+// only for the words that still have a live start.
+constexpr int kSearchProbe = 8;
+
+__global__ void __launch_bounds__(256)
+search_kernel(const uint32_t* __restrict__ plane, long long p0, long long nwords, DevCfg cfg,
+              RawHit* __restrict__ hits, unsigned long long hit_cap, unsigned long long* __restrict__ hit_count) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride) {
         const long long base = p0 + (w << 5);
         for (int p = 0; p < cfg.npre; p++) {
             uint32_t m = 0xFFFFFFFFu;
             const int nb = cfg.pre_nbits[p];
-            for (int k = 0; k < nb && m; k++) {
-                const uint32_t x = plane_window(plane, base + (long long)k * cfg.SL);
+            const int probe = nb < kSearchProbe ? nb : kSearchProbe;
+#pragma unroll
+            for (int k = 0; k < kSearchProbe; k++) {
+                if (k < probe) {
+                    const uint32_t x = plane_window2(plane, base + (long long)k * cfg.SL);
+                    m &= cfg.pre_bits[p][k] ? x : ~x;
+                }
+            }
+            if (m == 0) continue;
+            for (int k = probe; k < nb && m; k++) {
+                const uint32_t x = plane_window2(plane, base + (long long)k * cfg.SL);
                 m &= cfg.pre_bits[p][k] ? x : ~x;
             }
             while (m) {
@@ -66,45 +86,56 @@ __device__ __forceinline__ uint8_t gf_mul(const Gf32& g, uint8_t x, uint8_t y) {
     return g.exp[g.log[x] + g.log[y]];
 }
 
-// One CTA per candidate (grid-stride).  Thread j < packet_bytes gathers byte j of the packet
-// (8 strided plane bits, decode.go:363-366); thread 0 then runs the screens of every parser
-// registered under the candidate's preamble.
+constexpr int kExtractWarps = 8;
+
+// One WARP per candidate (grid-stride over warps).  Lane l gathers packet symbols l, l+32, ...
+// (decode.go:363-366: bit p of the packet is stream bit start + p*SL); a ballot turns 32 symbols into
+// 4 packet bytes.  Lane 0 then runs the screens of every parser filed under the candidate's preamble
+// with the CRC tables staged in shared memory, and the 160-byte record is written by all lanes.
 // If `r900_digits` is non-null it holds, per raw hit, the 42 payload digits computed by
 // r900_replay_kernel.
-__global__ void extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg,
-                               const RawHit* __restrict__ hits, unsigned long long hit_cap,
-                               const unsigned long long* __restrict__ hit_count,
-                               const uint16_t* __restrict__ crc_tables, Gf32 gf,
-                               const uint8_t* __restrict__ r900_digits, long long first_block,
-                               uint32_t flags, ertgpu_candidate* __restrict__ out,
-                               unsigned long long out_cap, unsigned long long* __restrict__ out_count,
-                               unsigned long long* __restrict__ valid_count) {
-    __shared__ uint8_t bytes[ERTGPU_MAX_PACKET_BYTES + 4];
+__global__ void __launch_bounds__(kExtractWarps * 32)
+extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, const RawHit* __restrict__ hits,
+               unsigned long long hit_cap, const unsigned long long* __restrict__ hit_count,
+               const uint16_t* __restrict__ crc_tables, Gf32 gf, const uint8_t* __restrict__ r900_digits,
+               long long first_block, uint32_t flags, ertgpu_candidate* __restrict__ out,
+               unsigned long long out_cap, unsigned long long* __restrict__ out_count,
+               unsigned long long* __restrict__ valid_count) {
+    __shared__ uint16_t tbl_s[ERTGPU_MAX_PROTOCOLS * 256];
+    __shared__ __align__(16) ertgpu_candidate rec_s[kExtractWarps];
+    for (int i = threadIdx.x; i < cfg.nproto * 256; i += blockDim.x) tbl_s[i] = crc_tables[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ertgpu_candidate* rec = &rec_s[warp];
+    uint8_t* bytes = rec->bytes;
     unsigned long long n = *hit_count;
     if (n > hit_cap) n = hit_cap;
-    for (unsigned long long c = blockIdx.x; c < n; c += gridDim.x) {
+    const unsigned long long wstride = (unsigned long long)gridDim.x * kExtractWarps;
+    for (unsigned long long c = (unsigned long long)blockIdx.x * kExtractWarps + warp; c < n; c += wstride) {
         const RawHit h = hits[c];
-        const int j = threadIdx.x;
-        if (j < ERTGPU_MAX_PACKET_BYTES) {
-            uint32_t v = 0;
-            if (j < cfg.packet_bytes) {
-                for (int k = 0; k < 8; k++) {
-                    const int sym = j * 8 + k;
-                    // a trailing partial byte is filled like a fresh d.pkt: PK%8 shifts only (decode.go:363-366)
-                    if (sym < cfg.PK) v = (v << 1) | plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL);
-                }
-            }
-            bytes[j] = (uint8_t)v;
+        const int nchunks = (cfg.PK + 31) >> 5;
+        for (int ch = 0; ch < nchunks; ch++) {
+            const int sym = ch * 32 + lane;
+            uint32_t bit = 0;
+            if (sym < cfg.PK) bit = plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL);
+            const uint32_t v = __brev(__ballot_sync(0xFFFFFFFFu, bit));  // MSB = symbol 32*ch
+            if (lane < 4 && ch * 4 + lane < ERTGPU_MAX_PACKET_BYTES) bytes[ch * 4 + lane] = (uint8_t)(v >> (24 - 8 * lane));
         }
-        __syncthreads();
-        if (j == 0) {
+        for (int q = nchunks * 4 + lane; q < ERTGPU_MAX_PACKET_BYTES; q += 32) bytes[q] = 0;
+        __syncwarp();
+        if (lane == 0) {
+            // a trailing partial byte holds its PK%8 bits in the LOW bits, like d.pkt after PK%8 shifts
+            // of a zeroed buffer (decode.go:363-366)
+            if (cfg.PK & 7) bytes[cfg.PK >> 3] = (uint8_t)(bytes[cfg.PK >> 3] >> (8 - (cfg.PK & 7)));
+            for (int q = cfg.packet_bytes; q < nchunks * 4 && q < ERTGPU_MAX_PACKET_BYTES; q++) bytes[q] = 0;
             uint32_t mask = 0;
-            const uint8_t* dig = r900_digits ? r900_digits + c * ERTGPU_R900_DIGITS : nullptr;
+            const bool has_dig = r900_digits != nullptr && cfg.pre_has_r900[h.preamble_id];
+            const uint8_t* dig = has_dig ? r900_digits + c * ERTGPU_R900_DIGITS : nullptr;
             for (int i = 0; i < cfg.nproto; i++) {
                 const DevProto& pr = cfg.proto[i];
                 if (pr.preamble_id != h.preamble_id) continue;
                 bool ok = false;
-                const uint16_t* tbl = crc_tables + 256 * pr.table;
+                const uint16_t* tbl = tbl_s + 256 * pr.table;
                 if (pr.check_kind == ERTGPU_CHECK_NONE) {
                     ok = true;
                 } else if (pr.check_kind == ERTGPU_CHECK_CRC16) {
@@ -133,24 +164,28 @@ __global__ void extract_kernel(const uint32_t* __restrict__ plane, long long p0,
                 }
                 if (ok) mask |= 1u << i;
             }
-            if (mask) atomicAdd(valid_count, 1ull);
-            if (mask || !(flags & ERTGPU_DECODE_ONLY_VALID)) {
-                const unsigned long long slot = atomicAdd(out_count, 1ull);
-                if (slot < out_cap) {
-                    ertgpu_candidate* o = out + slot;
-                    o->block = first_block + (long long)(h.s / (unsigned long long)cfg.BS);
-                    o->idx = (int32_t)(h.s % (unsigned long long)cfg.BS);
-                    o->preamble_id = h.preamble_id;
-                    o->check_mask = mask;
-                    o->flags = dig && cfg.pre_has_r900[h.preamble_id] ? ERTGPU_CAND_HAS_R900 : 0u;
-                    for (int q = 0; q < ERTGPU_MAX_PACKET_BYTES; q++) o->bytes[q] = bytes[q];
-                    for (int q = 0; q < ERTGPU_R900_DIGITS; q++)
-                        o->r900_digits[q] = (dig && cfg.pre_has_r900[h.preamble_id]) ? dig[q] : 0;
-                    o->pad[0] = o->pad[1] = 0;
-                }
-            }
+            rec->block = first_block + (long long)(h.s / (unsigned long long)cfg.BS);
+            rec->idx = (int32_t)(h.s % (unsigned long long)cfg.BS);
+            rec->preamble_id = h.preamble_id;
+            rec->check_mask = mask;
+            rec->flags = has_dig ? ERTGPU_CAND_HAS_R900 : 0u;
+            for (int q = 0; q < ERTGPU_R900_DIGITS; q++) rec->r900_digits[q] = has_dig ? dig[q] : 0;
+            rec->pad[0] = rec->pad[1] = 0;
         }
-        __syncthreads();
+        __syncwarp();
+        const uint32_t mask = rec->check_mask;
+        unsigned long long slot = ~0ull;
+        if (lane == 0) {
+            if (mask) atomicAdd(valid_count, 1ull);
+            if (mask || !(flags & ERTGPU_DECODE_ONLY_VALID)) slot = atomicAdd(out_count, 1ull);
+        }
+        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+        if (slot < out_cap) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(rec);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(out + slot);
+            for (int q = lane; q < (int)(sizeof(ertgpu_candidate) / 4); q += 32) dst[q] = src[q];
+        }
+        __syncwarp();
     }
 }
 
