@@ -214,11 +214,24 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
 
     // 2. preamble search over every start position of the call
     {
-        const int nthr = 256;
-        long long blocks = (nwords + nthr - 1) / nthr;
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        if (blocks < 1) blocks = 1;
-        search_kernel<<<(unsigned)blocks, nthr, 0, st>>>(plane, p0, nwords, c, h->d_hits, h->cand_cap, h->d_counters);
+        SearchParams sp;
+        if (make_search_params(c, p0, nwords, (long long)h->plane_words, &sp)) {
+            const size_t smem = (size_t)(kSearchTile + sp.halo_words) * sizeof(uint32_t);
+            long long tiles = (nwords + kSearchTile - 1) / kSearchTile;
+            unsigned grid = (unsigned)std::min<long long>(tiles, 148 * 4);
+            if (grid < 1) grid = 1;
+            switch (c.npre) {
+                case 1: search_kernel<1><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->cand_cap, h->d_counters); break;
+                case 2: search_kernel<2><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->cand_cap, h->d_counters); break;
+                case 3: search_kernel<3><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->cand_cap, h->d_counters); break;
+                default: search_kernel<4><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->cand_cap, h->d_counters); break;
+            }
+        } else {
+            const int nthr = 256;
+            long long blocks = std::min<long long>((nwords + nthr - 1) / nthr, 148 * 16);
+            if (blocks < 1) blocks = 1;
+            search_generic_kernel<<<(unsigned)blocks, nthr, 0, st>>>(plane, p0, nwords, c, h->d_hits, h->cand_cap, h->d_counters);
+        }
         CUDA_TRY(h, cudaGetLastError());
         h->launches++;
     }

@@ -13,47 +13,141 @@
 // of starts is the AND over the preamble bits k of (plane window at +k*SL) XNOR P[k].
 #pragma once
 
+#include <cstring>
+
 #include "demod_generic.cuh"
 #include "ert_common.cuh"
 
 namespace ert {
 
-// 32 consecutive plane bits starting at bit `pos` (first bit in the MSB), branch free
+// ---- Search -------------------------------------------------------------------------------
+//
+// A CTA stages a tile of the bit-plane (kSearchTile words of start positions + the halo the last
+// preamble bit reaches) in shared memory; a thread then tests 32 consecutive start positions at a
+// time.  For preamble bit k every start of the word looks at the SAME relative window: word offset
+// offw[k] and bit shift shk[k] are launch constants, so one test is 2 LDS + 1 funnel shift + 1 LOP3
+// per registered preamble (the window is shared by all preambles).  The first kSearchProbe bits are
+// tested unconditionally (no divergence: 1/256 of the starts survive on noise), the remaining bits
+// only for words that still have a live start.
+constexpr int kSearchThreads = 256;
+constexpr int kSearchTile = 2048;   // words of starts per CTA iteration
+constexpr int kSearchProbe = 8;
+constexpr int kSearchMaxPre = 4;
+
+struct SearchParams {
+    int32_t offw[ERTGPU_MAX_PREAMBLE];              // (sh0 + k*SL) >> 5
+    int32_t shk[ERTGPU_MAX_PREAMBLE];               // (sh0 + k*SL) & 31
+    uint32_t inv[kSearchMaxPre][ERTGPU_MAX_PREAMBLE];  // 0 where P[k]=1, ~0 where P[k]=0
+    int32_t nbits[kSearchMaxPre];
+    int32_t npre;
+    int32_t halo_words;
+    long long word0;   // plane word that holds the first start of the call
+    long long nwords;  // words of starts
+    long long plane_words;  // allocated words of the plane (reads beyond are zeros)
+};
+
+template <int NPRE>
+__global__ void __launch_bounds__(kSearchThreads)
+search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __restrict__ hits,
+              unsigned long long hit_cap, unsigned long long* __restrict__ hit_count) {
+    extern __shared__ uint32_t search_sm[];
+    const long long ntiles = (sp.nwords + kSearchTile - 1) / kSearchTile;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long t0 = tile * kSearchTile;
+        const int nload = kSearchTile + sp.halo_words;
+        __syncthreads();  // previous tile fully consumed
+        for (int i = threadIdx.x; i < nload; i += kSearchThreads) {
+            const long long wi = sp.word0 + t0 + i;
+            search_sm[i] = wi < sp.plane_words ? plane[wi] : 0u;
+        }
+        __syncthreads();
+        const int nhere = (int)((sp.nwords - t0 < kSearchTile) ? (sp.nwords - t0) : kSearchTile);
+        for (int j = threadIdx.x; j < nhere; j += kSearchThreads) {
+            uint32_t m[NPRE];
+#pragma unroll
+            for (int p = 0; p < NPRE; p++) m[p] = 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < kSearchProbe; k++) {
+                const uint32_t x = __funnelshift_l(search_sm[j + sp.offw[k] + 1], search_sm[j + sp.offw[k]], sp.shk[k]);
+#pragma unroll
+                for (int p = 0; p < NPRE; p++) m[p] &= x ^ sp.inv[p][k];
+            }
+#pragma unroll
+            for (int p = 0; p < NPRE; p++) {
+                uint32_t mm = m[p];
+                if (mm == 0) continue;
+                for (int k = kSearchProbe; k < sp.nbits[p] && mm; k++) {
+                    const uint32_t x = __funnelshift_l(search_sm[j + sp.offw[k] + 1], search_sm[j + sp.offw[k]], sp.shk[k]);
+                    mm &= x ^ sp.inv[p][k];
+                }
+                if (mm == 0) continue;
+                // one reservation per word of starts (same-address atomics serialise in L2)
+                unsigned long long slot = atomicAdd(hit_count, (unsigned long long)__popc(mm));
+                while (mm) {
+                    const int lead = __clz(mm);  // MSB = first start of the word
+                    mm &= ~(0x80000000u >> lead);
+                    if (slot < hit_cap) {
+                        RawHit h;
+                        h.s = (unsigned long long)(((t0 + j) << 5) + lead);
+                        h.preamble_id = p;
+                        h.pad = 0;
+                        hits[slot] = h;
+                    }
+                    slot++;
+                }
+            }
+        }
+    }
+}
+
+// host: fill the launch constants.  p0 = plane bit of start 0.
+inline bool make_search_params(const DevCfg& c, long long p0, long long nwords, long long plane_words, SearchParams* sp) {
+    if (c.npre > kSearchMaxPre) return false;
+    memset(sp, 0, sizeof(*sp));
+    const int sh0 = (int)(p0 & 31);
+    int maxbits = 0;
+    for (int p = 0; p < c.npre; p++) {
+        if (c.pre_nbits[p] < kSearchProbe) return false;
+        sp->nbits[p] = c.pre_nbits[p];
+        if (c.pre_nbits[p] > maxbits) maxbits = c.pre_nbits[p];
+        for (int k = 0; k < ERTGPU_MAX_PREAMBLE; k++)
+            sp->inv[p][k] = (k < c.pre_nbits[p]) ? (c.pre_bits[p][k] ? 0u : 0xFFFFFFFFu) : 0u;
+    }
+    for (int p = c.npre; p < kSearchMaxPre; p++) sp->nbits[p] = 0;
+    for (int k = 0; k < ERTGPU_MAX_PREAMBLE; k++) {
+        const long long off = sh0 + (long long)k * c.SL;
+        sp->offw[k] = (int32_t)(off >> 5);
+        sp->shk[k] = (int32_t)(off & 31);
+    }
+    sp->npre = c.npre;
+    sp->halo_words = (int32_t)(((sh0 + (long long)(maxbits - 1) * c.SL) >> 5) + 2);
+    sp->word0 = p0 >> 5;
+    sp->nwords = nwords;
+    sp->plane_words = plane_words;
+    return true;
+}
+
+// slow path kept for more than kSearchMaxPre preambles or very short preambles
 __device__ __forceinline__ uint32_t plane_window2(const uint32_t* __restrict__ plane, long long pos) {
     const long long w = pos >> 5;
     return __funnelshift_l(plane[w + 1], plane[w], (int)(pos & 31));
 }
 
-// grid-stride over words of 32 start positions; plane bit index of start s is p0 + s.
-// Two phases per preamble: the first kSearchProbe preamble bits are tested unconditionally
-// (straight-line code, no divergence: 1/256 of the starts survive on noise), the remaining bits
-// only for the words that still have a live start.
-constexpr int kSearchProbe = 8;
-
 __global__ void __launch_bounds__(256)
-search_kernel(const uint32_t* __restrict__ plane, long long p0, long long nwords, DevCfg cfg,
-              RawHit* __restrict__ hits, unsigned long long hit_cap, unsigned long long* __restrict__ hit_count) {
+search_generic_kernel(const uint32_t* __restrict__ plane, long long p0, long long nwords, DevCfg cfg,
+                      RawHit* __restrict__ hits, unsigned long long hit_cap, unsigned long long* __restrict__ hit_count) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride) {
         const long long base = p0 + (w << 5);
         for (int p = 0; p < cfg.npre; p++) {
             uint32_t m = 0xFFFFFFFFu;
             const int nb = cfg.pre_nbits[p];
-            const int probe = nb < kSearchProbe ? nb : kSearchProbe;
-#pragma unroll
-            for (int k = 0; k < kSearchProbe; k++) {
-                if (k < probe) {
-                    const uint32_t x = plane_window2(plane, base + (long long)k * cfg.SL);
-                    m &= cfg.pre_bits[p][k] ? x : ~x;
-                }
-            }
-            if (m == 0) continue;
-            for (int k = probe; k < nb && m; k++) {
+            for (int k = 0; k < nb && m; k++) {
                 const uint32_t x = plane_window2(plane, base + (long long)k * cfg.SL);
                 m &= cfg.pre_bits[p][k] ? x : ~x;
             }
             while (m) {
-                const int lead = __clz(m);  // MSB = first start of the word
+                const int lead = __clz(m);
                 m &= ~(0x80000000u >> lead);
                 const unsigned long long slot = atomicAdd(hit_count, 1ull);
                 if (slot < hit_cap) {
@@ -110,82 +204,100 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, con
     uint8_t* bytes = rec->bytes;
     unsigned long long n = *hit_count;
     if (n > hit_cap) n = hit_cap;
-    const unsigned long long wstride = (unsigned long long)gridDim.x * kExtractWarps;
-    for (unsigned long long c = (unsigned long long)blockIdx.x * kExtractWarps + warp; c < n; c += wstride) {
-        const RawHit h = hits[c];
-        const int nchunks = (cfg.PK + 31) >> 5;
-        for (int ch = 0; ch < nchunks; ch++) {
-            const int sym = ch * 32 + lane;
-            uint32_t bit = 0;
-            if (sym < cfg.PK) bit = plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL);
-            const uint32_t v = __brev(__ballot_sync(0xFFFFFFFFu, bit));  // MSB = symbol 32*ch
-            if (lane < 4 && ch * 4 + lane < ERTGPU_MAX_PACKET_BYTES) bytes[ch * 4 + lane] = (uint8_t)(v >> (24 - 8 * lane));
-        }
-        for (int q = nchunks * 4 + lane; q < ERTGPU_MAX_PACKET_BYTES; q += 32) bytes[q] = 0;
-        __syncwarp();
-        if (lane == 0) {
-            // a trailing partial byte holds its PK%8 bits in the LOW bits, like d.pkt after PK%8 shifts
-            // of a zeroed buffer (decode.go:363-366)
-            if (cfg.PK & 7) bytes[cfg.PK >> 3] = (uint8_t)(bytes[cfg.PK >> 3] >> (8 - (cfg.PK & 7)));
-            for (int q = cfg.packet_bytes; q < nchunks * 4 && q < ERTGPU_MAX_PACKET_BYTES; q++) bytes[q] = 0;
-            uint32_t mask = 0;
-            const bool has_dig = r900_digits != nullptr && cfg.pre_has_r900[h.preamble_id];
-            const uint8_t* dig = has_dig ? r900_digits + c * ERTGPU_R900_DIGITS : nullptr;
-            for (int i = 0; i < cfg.nproto; i++) {
-                const DevProto& pr = cfg.proto[i];
-                if (pr.preamble_id != h.preamble_id) continue;
-                bool ok = false;
-                const uint16_t* tbl = tbl_s + 256 * pr.table;
-                if (pr.check_kind == ERTGPU_CHECK_NONE) {
-                    ok = true;
-                } else if (pr.check_kind == ERTGPU_CHECK_CRC16) {
-                    ok = crc16(tbl, pr.crc_init, bytes + pr.crc_from, pr.crc_to - pr.crc_from) == pr.crc_residue;
-                } else if (pr.check_kind == ERTGPU_CHECK_IDM) {
-                    ok = crc16(tbl, pr.crc_init, bytes + 4, 88) == pr.crc_residue;  // idm.go:77
-                    if (ok) {
-                        uint8_t buf[6] = {bytes[9], bytes[10], bytes[11], bytes[12], bytes[88], bytes[89]};
-                        ok = crc16(tbl, pr.crc_init, buf, 6) == pr.crc_residue;     // idm.go:82-87
-                    }
-                } else if (pr.check_kind == ERTGPU_CHECK_R900 && dig) {
-                    uint8_t msg[31];
-                    for (int q = 0; q < 31; q++) msg[q] = 0;
-                    ok = true;
-                    for (int q = 0; q < 21 && ok; q++) {            // r900.go:199-207
-                        const int sym = dig[2 * q] * 6 + dig[2 * q + 1];
-                        if (sym > 31) ok = false;
-                        msg[q < 16 ? q : q + 10] = (uint8_t)sym;    // r900.go:215-216
-                    }
-                    for (int s = 0; s < 5 && ok; s++) {             // gf.go:163-169, Syndrome(msg,5,29)
-                        const uint8_t root = gf.exp[(29 + s) % 31];
-                        uint8_t syn = msg[0];
-                        for (int q = 1; q < 31; q++) syn = gf_mul(gf, syn, root) ^ msg[q];
-                        if (syn) ok = false;
-                    }
-                }
-                if (ok) mask |= 1u << i;
+    __shared__ unsigned long long base_s;
+    __shared__ uint32_t want_s[kExtractWarps];  // bit0: record is emitted, bit1: passed a screen
+    const unsigned long long cstride = (unsigned long long)gridDim.x * kExtractWarps;
+    // all warps of the CTA run the same number of rounds so that the slot reservation can be one
+    // atomic per CTA round (same-address atomics serialise in L2)
+    for (unsigned long long c0 = (unsigned long long)blockIdx.x * kExtractWarps; c0 < n; c0 += cstride) {
+        const unsigned long long c = c0 + warp;
+        const bool have = c < n;
+        RawHit h;
+        h.s = 0; h.preamble_id = 0; h.pad = 0;
+        if (have) h = hits[c];
+        if (have) {
+            const int nchunks = (cfg.PK + 31) >> 5;
+            for (int ch = 0; ch < nchunks; ch++) {
+                const int sym = ch * 32 + lane;
+                uint32_t bit = 0;
+                if (sym < cfg.PK) bit = plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL);
+                const uint32_t v = __brev(__ballot_sync(0xFFFFFFFFu, bit));  // MSB = symbol 32*ch
+                if (lane < 4 && ch * 4 + lane < ERTGPU_MAX_PACKET_BYTES) bytes[ch * 4 + lane] = (uint8_t)(v >> (24 - 8 * lane));
             }
-            rec->block = first_block + (long long)(h.s / (unsigned long long)cfg.BS);
-            rec->idx = (int32_t)(h.s % (unsigned long long)cfg.BS);
-            rec->preamble_id = h.preamble_id;
-            rec->check_mask = mask;
-            rec->flags = has_dig ? ERTGPU_CAND_HAS_R900 : 0u;
-            for (int q = 0; q < ERTGPU_R900_DIGITS; q++) rec->r900_digits[q] = has_dig ? dig[q] : 0;
-            rec->pad[0] = rec->pad[1] = 0;
+            for (int q = nchunks * 4 + lane; q < ERTGPU_MAX_PACKET_BYTES; q += 32) bytes[q] = 0;
+            __syncwarp();
+            if (lane == 0) {
+                // a trailing partial byte holds its PK%8 bits in the LOW bits, like d.pkt after PK%8 shifts
+                // of a zeroed buffer (decode.go:363-366)
+                if (cfg.PK & 7) bytes[cfg.PK >> 3] = (uint8_t)(bytes[cfg.PK >> 3] >> (8 - (cfg.PK & 7)));
+                for (int q = cfg.packet_bytes; q < nchunks * 4 && q < ERTGPU_MAX_PACKET_BYTES; q++) bytes[q] = 0;
+                uint32_t mask = 0;
+                const bool has_dig = r900_digits != nullptr && cfg.pre_has_r900[h.preamble_id];
+                const uint8_t* dig = has_dig ? r900_digits + c * ERTGPU_R900_DIGITS : nullptr;
+                for (int i = 0; i < cfg.nproto; i++) {
+                    const DevProto& pr = cfg.proto[i];
+                    if (pr.preamble_id != h.preamble_id) continue;
+                    bool ok = false;
+                    const uint16_t* tbl = tbl_s + 256 * pr.table;
+                    if (pr.check_kind == ERTGPU_CHECK_NONE) {
+                        ok = true;
+                    } else if (pr.check_kind == ERTGPU_CHECK_CRC16) {
+                        ok = crc16(tbl, pr.crc_init, bytes + pr.crc_from, pr.crc_to - pr.crc_from) == pr.crc_residue;
+                    } else if (pr.check_kind == ERTGPU_CHECK_IDM) {
+                        ok = crc16(tbl, pr.crc_init, bytes + 4, 88) == pr.crc_residue;  // idm.go:77
+                        if (ok) {
+                            uint8_t buf[6] = {bytes[9], bytes[10], bytes[11], bytes[12], bytes[88], bytes[89]};
+                            ok = crc16(tbl, pr.crc_init, buf, 6) == pr.crc_residue;     // idm.go:82-87
+                        }
+                    } else if (pr.check_kind == ERTGPU_CHECK_R900 && dig) {
+                        uint8_t msg[31];
+                        for (int q = 0; q < 31; q++) msg[q] = 0;
+                        ok = true;
+                        for (int q = 0; q < 21 && ok; q++) {            // r900.go:199-207
+                            const int sym = dig[2 * q] * 6 + dig[2 * q + 1];
+                            if (sym > 31) ok = false;
+                            msg[q < 16 ? q : q + 10] = (uint8_t)sym;    // r900.go:215-216
+                        }
+                        for (int s = 0; s < 5 && ok; s++) {             // gf.go:163-169, Syndrome(msg,5,29)
+                            const uint8_t root = gf.exp[(29 + s) % 31];
+                            uint8_t syn = msg[0];
+                            for (int q = 1; q < 31; q++) syn = gf_mul(gf, syn, root) ^ msg[q];
+                            if (syn) ok = false;
+                        }
+                    }
+                    if (ok) mask |= 1u << i;
+                }
+                rec->block = first_block + (long long)(h.s / (unsigned long long)cfg.BS);
+                rec->idx = (int32_t)(h.s % (unsigned long long)cfg.BS);
+                rec->preamble_id = h.preamble_id;
+                rec->check_mask = mask;
+                rec->flags = has_dig ? ERTGPU_CAND_HAS_R900 : 0u;
+                for (int q = 0; q < ERTGPU_R900_DIGITS; q++) rec->r900_digits[q] = has_dig ? dig[q] : 0;
+                rec->pad[0] = rec->pad[1] = 0;
+                want_s[warp] = ((mask || !(flags & ERTGPU_DECODE_ONLY_VALID)) ? 1u : 0u) | (mask ? 2u : 0u);
+            }
+        } else if (lane == 0) {
+            want_s[warp] = 0;
         }
-        __syncwarp();
-        const uint32_t mask = rec->check_mask;
-        unsigned long long slot = ~0ull;
-        if (lane == 0) {
-            if (mask) atomicAdd(valid_count, 1ull);
-            if (mask || !(flags & ERTGPU_DECODE_ONLY_VALID)) slot = atomicAdd(out_count, 1ull);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned nout = 0, nvalid = 0;
+            for (int q = 0; q < kExtractWarps; q++) { nout += want_s[q] & 1u; nvalid += (want_s[q] >> 1) & 1u; }
+            if (nvalid) atomicAdd(valid_count, (unsigned long long)nvalid);
+            base_s = nout ? atomicAdd(out_count, (unsigned long long)nout) : 0ull;
         }
-        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
-        if (slot < out_cap) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(rec);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(out + slot);
-            for (int q = lane; q < (int)(sizeof(ertgpu_candidate) / 4); q += 32) dst[q] = src[q];
+        __syncthreads();
+        if (want_s[warp] & 1u) {
+            unsigned before = 0;
+            for (int q = 0; q < warp; q++) before += want_s[q] & 1u;
+            const unsigned long long slot = base_s + before;
+            if (slot < out_cap) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(rec);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(out + slot);
+                for (int q = lane; q < (int)(sizeof(ertgpu_candidate) / 4); q += 32) dst[q] = src[q];
+            }
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
