@@ -215,8 +215,8 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     // 2. preamble search over every start position of the call
     {
         SearchParams sp;
-        if (make_search_params(c, p0, nwords, (long long)h->plane_words, &sp)) {
-            const size_t smem = (size_t)(kSearchTile + sp.halo_words) * sizeof(uint32_t);
+        if (make_search_params(c, p0, nwords, &sp)) {
+            const size_t smem = 0;
             long long tiles = (nwords + kSearchTile - 1) / kSearchTile;
             unsigned grid = (unsigned)std::min<long long>(tiles, 148 * 4);
             if (grid < 1) grid = 1;
@@ -517,7 +517,7 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
     CUDA_TRY(h, cudaMalloc(&h->d_crc, tables.size() * sizeof(uint16_t)));
     CUDA_TRY(h, cudaMemcpy(h->d_crc, tables.data(), tables.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
 
-    h->plane_words = (size_t)d.hist_words + (size_t)max_blocks_per_call * d.words_per_block + 8;
+    h->plane_words = (size_t)d.hist_words + (size_t)max_blocks_per_call * d.words_per_block + kSearchTile + kSearchMaxHalo + 8;
     for (int k = 0; k < 2; k++) {
         CUDA_TRY(h, cudaMalloc(&h->d_plane[k], h->plane_words * sizeof(uint32_t)));
         CUDA_TRY(h, cudaMemset(h->d_plane[k], 0, h->plane_words * sizeof(uint32_t)));

@@ -15,6 +15,7 @@
 
 #include <cstring>
 
+#include "demod_fast.cuh"
 #include "demod_generic.cuh"
 #include "ert_common.cuh"
 
@@ -31,44 +32,69 @@ namespace ert {
 // only for words that still have a live start.
 constexpr int kSearchThreads = 256;
 constexpr int kSearchTile = 2048;   // words of starts per CTA iteration
-constexpr int kSearchProbe = 8;
+constexpr int kSearchProbe = 12;    // preamble bits tested unconditionally
 constexpr int kSearchMaxPre = 4;
+constexpr int kSearchMaxHalo = 160; // words: (31*SL + 31)/32 + 2 for SL <= 160
 
 struct SearchParams {
-    int32_t offw[ERTGPU_MAX_PREAMBLE];              // (sh0 + k*SL) >> 5
+    int32_t offb[ERTGPU_MAX_PREAMBLE];              // 4 * ((sh0 + k*SL) >> 5): byte offset of the window's first word
     int32_t shk[ERTGPU_MAX_PREAMBLE];               // (sh0 + k*SL) & 31
     uint32_t inv[kSearchMaxPre][ERTGPU_MAX_PREAMBLE];  // 0 where P[k]=1, ~0 where P[k]=0
     int32_t nbits[kSearchMaxPre];
     int32_t npre;
     int32_t halo_words;
-    long long word0;   // plane word that holds the first start of the call
     long long nwords;  // words of starts
-    long long plane_words;  // allocated words of the plane (reads beyond are zeros)
 };
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// The plane's first start lies in word 0 (p0 < 32), so tile t starts at plane word t*kSearchTile:
+// 16-byte aligned, fetched with one cp.async.bulk per tile into a 2-stage ring (the plane is
+// allocated with kSearchTile + kSearchMaxHalo words of slack so the last tile can over-read).
 template <int NPRE>
 __global__ void __launch_bounds__(kSearchThreads)
 search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __restrict__ hits,
               unsigned long long hit_cap, unsigned long long* __restrict__ hit_count) {
-    extern __shared__ uint32_t search_sm[];
+    __shared__ __align__(128) uint32_t buf[2][kSearchTile + kSearchMaxHalo];
+    __shared__ __align__(8) unsigned long long bars[2];
     const long long ntiles = (sp.nwords + kSearchTile - 1) / kSearchTile;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t bar0 = smem_u32(&bars[0]);
+    const uint32_t nload_bytes = (uint32_t)((kSearchTile + sp.halo_words + 3) & ~3) * 4u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long tile, int st) {
+        mbar_arrive_expect_tx(bar0 + 8 * st, nload_bytes);
+        bulk_g2s(smem_u32(&buf[st][0]), plane + tile * kSearchTile, nload_bytes, bar0 + 8 * st);
+    };
+    if (threadIdx.x == 0 && blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    uint32_t phases = 0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int st = it & 1;
+        const long long next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) issue(next, st ^ 1);  // that stage was released by the barrier below
+        mbar_wait(bar0 + 8 * st, (phases >> st) & 1u);
+        phases ^= 1u << st;
         const long long t0 = tile * kSearchTile;
-        const int nload = kSearchTile + sp.halo_words;
-        __syncthreads();  // previous tile fully consumed
-        for (int i = threadIdx.x; i < nload; i += kSearchThreads) {
-            const long long wi = sp.word0 + t0 + i;
-            search_sm[i] = wi < sp.plane_words ? plane[wi] : 0u;
-        }
-        __syncthreads();
         const int nhere = (int)((sp.nwords - t0 < kSearchTile) ? (sp.nwords - t0) : kSearchTile);
+        const uint32_t base = smem_u32(&buf[st][0]);
         for (int j = threadIdx.x; j < nhere; j += kSearchThreads) {
+            const uint32_t row = base + 4u * (uint32_t)j;
             uint32_t m[NPRE];
 #pragma unroll
             for (int p = 0; p < NPRE; p++) m[p] = 0xFFFFFFFFu;
 #pragma unroll
             for (int k = 0; k < kSearchProbe; k++) {
-                const uint32_t x = __funnelshift_l(search_sm[j + sp.offw[k] + 1], search_sm[j + sp.offw[k]], sp.shk[k]);
+                const uint32_t a = row + (uint32_t)sp.offb[k];
+                const uint32_t x = __funnelshift_l(lds_u32(a + 4), lds_u32(a), sp.shk[k]);
 #pragma unroll
                 for (int p = 0; p < NPRE; p++) m[p] &= x ^ sp.inv[p][k];
             }
@@ -77,7 +103,8 @@ search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __res
                 uint32_t mm = m[p];
                 if (mm == 0) continue;
                 for (int k = kSearchProbe; k < sp.nbits[p] && mm; k++) {
-                    const uint32_t x = __funnelshift_l(search_sm[j + sp.offw[k] + 1], search_sm[j + sp.offw[k]], sp.shk[k]);
+                    const uint32_t a = row + (uint32_t)sp.offb[k];
+                    const uint32_t x = __funnelshift_l(lds_u32(a + 4), lds_u32(a), sp.shk[k]);
                     mm &= x ^ sp.inv[p][k];
                 }
                 if (mm == 0) continue;
@@ -97,14 +124,15 @@ search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __res
                 }
             }
         }
+        __syncthreads();  // everyone is done with buf[st]: it may be refilled next iteration
     }
 }
 
-// host: fill the launch constants.  p0 = plane bit of start 0.
-inline bool make_search_params(const DevCfg& c, long long p0, long long nwords, long long plane_words, SearchParams* sp) {
-    if (c.npre > kSearchMaxPre) return false;
+// host: fill the launch constants.  p0 = plane bit of start 0 (must lie in word 0).
+inline bool make_search_params(const DevCfg& c, long long p0, long long nwords, SearchParams* sp) {
+    if (c.npre > kSearchMaxPre || p0 < 0 || p0 >= 32) return false;
     memset(sp, 0, sizeof(*sp));
-    const int sh0 = (int)(p0 & 31);
+    const int sh0 = (int)p0;
     int maxbits = 0;
     for (int p = 0; p < c.npre; p++) {
         if (c.pre_nbits[p] < kSearchProbe) return false;
@@ -113,17 +141,15 @@ inline bool make_search_params(const DevCfg& c, long long p0, long long nwords, 
         for (int k = 0; k < ERTGPU_MAX_PREAMBLE; k++)
             sp->inv[p][k] = (k < c.pre_nbits[p]) ? (c.pre_bits[p][k] ? 0u : 0xFFFFFFFFu) : 0u;
     }
-    for (int p = c.npre; p < kSearchMaxPre; p++) sp->nbits[p] = 0;
     for (int k = 0; k < ERTGPU_MAX_PREAMBLE; k++) {
         const long long off = sh0 + (long long)k * c.SL;
-        sp->offw[k] = (int32_t)(off >> 5);
+        sp->offb[k] = (int32_t)((off >> 5) * 4);
         sp->shk[k] = (int32_t)(off & 31);
     }
     sp->npre = c.npre;
     sp->halo_words = (int32_t)(((sh0 + (long long)(maxbits - 1) * c.SL) >> 5) + 2);
-    sp->word0 = p0 >> 5;
+    if (sp->halo_words > kSearchMaxHalo) return false;
     sp->nwords = nwords;
-    sp->plane_words = plane_words;
     return true;
 }
 
