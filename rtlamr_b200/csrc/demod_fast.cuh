@@ -8,21 +8,28 @@
 //  * One thread per reference block ("chain"); a warp owns 32 consecutive blocks.  The float32
 //    running sum of Filter is sequential within a block and restarts at every block
 //    (decode.go:232-236), so this is the only parallelism that keeps the sign bits exact.
-//  * Per sample: csum c += m; chip sum A = c - c[CL ago]; filter f = A[CL ago] - A; the two
-//    histories are rings of CL values each held in REGISTERS: the step loop is unrolled CL times
-//    so every ring slot is a fixed register (no indexing, no shared-memory traffic).
+//  * Per sample: running sum c += m; chip sum A = c - c[CL steps ago]; filter f = A[CL steps ago] - A.
+//    Both histories are rings held in REGISTERS.  The rings have L > CL slots (L = the unrolled
+//    body length): a new value is born into the slot that died L - CL steps earlier, so no value
+//    ever has to be moved -- every ring slot is a fixed register and the steady state is
+//    2 PRMT + 2 LDS + 4 FADD + 1 SHF per sample.
 //  * Magnitude lut[I] + lut[Q]: the 256-entry table is replicated per lane in shared memory as
 //    [value][lane] with a 256-byte row pitch, so a lookup address is ONE byte-permute
 //    (PRMT: {lane*4, value, base>>16}) and the 32 lanes always hit 32 different banks.  Column 32
-//    of every row holds 0.0f: the first block of a stream reads its SL lead-in magnitudes there
-//    (the reference's Signal buffer starts as zeros, decode.go:144).
-//  * IQ bytes reach the thread that needs them through shared memory: each lane issues one
-//    cp.async.bulk (TMA bulk copy, 2*CL bytes = one unrolled loop body's worth of its own chain)
-//    per body into a 2-stage ring, completion on an mbarrier; rows are padded to an odd number
-//    of 16-byte units so the per-lane LDS.128 reads are bank-conflict free.  HBM is read in
-//    whole 32-byte sectors, each byte once.
+//    of every row holds 0.0f: samples that must not contribute (the alignment pad in front of the
+//    lead-in, and the lead-in of the first block of a stream, whose Signal buffer starts as zeros,
+//    decode.go:144) are looked up there.
+//  * IQ bytes reach the thread that needs them through shared memory: body t of a warp's 32 chains
+//    is one [32 rows][2*L bytes] box of the IQ matrix (row = reference block), a single TMA tile
+//    load (cp.async.bulk.tensor.2d) issued by one lane into a 2-stage ring with an mbarrier per
+//    stage.  L/8 is odd, so rows have an odd 16-byte pitch and the per-lane LDS.128 reads are bank
+//    conflict free.  HBM is read in whole sectors, each byte once.
 //  * Sign bits are shifted into words with one funnel shift per sample and appended to the
 //    per-block bit-plane row.
+//
+// Stream of one chain, in steps: [pad = 2L - SL zero-magnitude steps][SL lead-in samples = tail of the
+// previous block][BS samples of the block]; bodies 0 and 1 are pad + lead-in, f[0] is produced by the
+// last step of body 1, bodies >= 2 produce L bits each.
 #pragma once
 
 #include <cuda.h>
@@ -31,7 +38,6 @@
 
 namespace ert {
 
-constexpr int kFastWarpChains = 32;
 constexpr int kLutBytes = 65536;  // 256 rows x 256 B (lanes 0..31 + zero column at byte 128)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,17 +84,24 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     return v;
 }
 
+// body length for a chip length: the smallest L >= CL + 1 with L % 8 == 0 and L / 8 odd
+constexpr int fast_body_len(int CL) {
+    int L = ((CL + 1 + 7) / 8) * 8;
+    if (((L / 8) & 1) == 0) L += 8;
+    return L;
+}
+
 template <int CL>
 struct FastGeom {
-    static constexpr int kRowBytes = 2 * CL;                       // one body's IQ bytes per chain
-    static constexpr int kRowUnits = kRowBytes / 16;
-    static constexpr int kStrideUnits = kRowUnits | 1;             // odd pitch in 16-byte units: conflict-free LDS.128
-    static constexpr int kStrideBytes = kStrideUnits * 16;
-    static constexpr int kStageBytes = 32 * kStrideBytes;
-    static constexpr int kWarpBytes = 2 * kStageBytes;             // 2-stage ring
-    static constexpr int kFullWords = CL / 32;                     // whole output words per body
-    static constexpr int kTailBits = CL % 32;
-    static_assert(CL % 8 == 0, "fast kernel needs CL % 8 == 0 (16-byte rows, 8 samples per LDS.128)");
+    static constexpr int L = fast_body_len(CL);
+    static constexpr int kPad = 2 * L - 2 * CL;        // zero-magnitude steps in front of the lead-in
+    static constexpr int kRowBytes = 2 * L;            // one body's IQ bytes per chain
+    static constexpr int kRowUnits = kRowBytes / 16;   // odd: conflict-free LDS.128
+    static constexpr int kStageBytes = 32 * kRowBytes;
+    static constexpr int kWarpBytes = 2 * kStageBytes;  // 2-stage ring
+    static constexpr int kFullWords = L / 32;           // whole output words per body
+    static constexpr int kTailBits = L % 32;
+    static_assert(L % 8 == 0 && (kRowUnits & 1) == 1 && L > CL && kPad % 8 == 0 && kPad < L, "bad body length");
 };
 
 // smem map (byte offsets inside the dynamic segment, computed at run time):
@@ -101,6 +114,7 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
                   const float* __restrict__ lut_g, uint32_t* __restrict__ plane_out, long long nblocks, int BS,
                   unsigned long long* __restrict__ tile_counter) {
     using G = FastGeom<CL>;
+    constexpr int L = G::L;
     extern __shared__ __align__(128) uint8_t fast_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t sbase = smem_u32(fast_smem);
@@ -125,15 +139,13 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
     }
     __syncthreads();
 
-    const int SL = 2 * CL;
-    const int wpb = BS >> 5;                              // words per block
-    const int nbody = (SL + BS - 1 + CL - 1) / CL;        // bodies of CL steps covering steps 0..SL+BS-2
-    const int chain_units = (2 * (SL + BS)) >> 4;         // lead-in + block, in 16-byte units
+    const int wpb = BS >> 5;                         // words per block
+    const int nbody = (2 * L + BS - 1 + L - 1) / L;  // bodies covering steps 0 .. 2L+BS-2
     const long long ntiles = (nblocks + 31) / 32;
     const uint32_t lo_main = lut_base | (uint32_t)(lane * 4);
-    const uint32_t row = stage0 + lane * G::kStrideBytes;
-    const bool have_hist = hist_valid >= SL;
-    const uint8_t* hist_lead = hist + 2ll * (hist_samples - SL);
+    const uint32_t lo_zero = lut_base | 128u;
+    const uint32_t row = stage0 + lane * G::kRowBytes;
+    const bool have_hist = hist_valid >= 2 * L;      // hist_valid is 0 or >= BlockSize
     uint32_t phases = 0;  // bit s = parity to wait for on stage s
 
     for (;;) {
@@ -144,87 +156,98 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
 
         long long b = (long long)tile * 32 + lane;
         const bool live = b < nblocks;
-        if (!live) b = nblocks - 1;  // duplicate a valid chain, results discarded
-        // The chain's bytes: bodies 0,1 are the SL lead-in samples (the tail of the previous
-        // block), bodies >= 2 the block itself -- one contiguous range except for block 0 of the
-        // call, whose lead-in lives in the history buffer (or is all-zero magnitude at stream start).
-        const uint32_t blk16 = (uint32_t)((b * 2ll * BS) >> 4);  // block start in 16-byte units
+        if (!live) b = nblocks - 1;  // the lane-copy path needs a valid source; results are discarded
         const bool first = (b == 0);
-        const uint32_t lo_lead = (first && !have_hist) ? (lut_base | 128u) : lo_main;
-        // Body t of the 32 chains of this work tile = one [32 rows][2*CL bytes] box of the IQ
-        // matrix (row = reference block, BlockSize2 bytes per row): a single TMA tile load issued
-        // by one lane.  Rows past the end of the call and columns past the end of a row are
-        // zero-filled by the TMA unit (the steps that read them produce no output).
-        // The first work tile of a call is the exception: block 0 takes its lead-in from the
-        // history buffer, so that tile uses one 1D bulk copy per lane instead.
+        // lead-in of the stream's very first block: magnitude 0.0 (zero column)
+        const uint32_t lo_lead = (first && !have_hist) ? lo_zero : lo_main;
+
+        // Body t of the 32 chains of this work tile = one [32 rows][2L bytes] box of the IQ matrix:
+        // bodies 0,1 come from the tail of the previous row (block), bodies >= 2 from the row itself.
+        // Rows past the end of the call and columns past the end of a row are zero-filled by the TMA
+        // unit (the steps that read them produce no output).  The first work tile of a call is the
+        // exception: block 0 takes its lead-in from the history buffer, so that tile uses one 1D bulk
+        // copy per lane instead.
         const bool lane_copies = (tile == 0);
         auto issue = [&](int t) {
             if (t >= nbody) return;
             const uint32_t bar = bar0 + (t & 1) * 8;
             if (!lane_copies) {
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(bar, 32u * G::kStrideBytes);
+                    mbar_arrive_expect_tx(bar, 32u * G::kRowBytes);
                     const int x = (t < 2) ? 2 * BS - 2 * G::kRowBytes + t * G::kRowBytes : (t - 2) * G::kRowBytes;
                     const int y = (int)(tile * 32) - (t < 2 ? 1 : 0);
                     tma_load_2d(stage0 + (t & 1) * G::kStageBytes, &iq_map, x, y, bar);
                 }
                 return;
             }
-            const int off16 = t * G::kRowUnits;
-            int n16 = chain_units - off16;
-            if (n16 > G::kRowUnits) n16 = G::kRowUnits;
+            // stream byte offset of body t relative to the block start: (t - 2) * 2L
+            const long long off = (long long)(t - 2) * G::kRowBytes;
+            long long n = 2ll * BS - off;  // bytes left in the block
+            if (n > G::kRowBytes) n = G::kRowBytes;
             const uint8_t* src;
-            if (t < 2 && first) src = have_hist ? hist_lead + 16ll * off16 : iq;
-            else src = iq + 16ll * ((long long)blk16 + off16 - 2 * G::kRowUnits);
-            if (lane == 0) mbar_arrive_expect_tx(bar, 32u * (uint32_t)n16 * 16u);
+            if (t < 2 && first) src = have_hist ? hist + 2ll * hist_samples + off : iq;  // off < 0: tail of the history
+            else src = iq + b * 2ll * BS + off;
+            if (lane == 0) mbar_arrive_expect_tx(bar, 32u * (uint32_t)n);
             __syncwarp();
-            bulk_g2s(row + (t & 1) * G::kStageBytes, src, (uint32_t)n16 * 16u, bar);
+            bulk_g2s(row + (t & 1) * G::kStageBytes, src, (uint32_t)n, bar);
         };
         issue(0);
         issue(1);
 
-        float cr[CL], ar[CL];
+        float cr[L], ar[L];
 #pragma unroll
-        for (int j = 0; j < CL; j++) { cr[j] = 0.0f; ar[j] = 0.0f; }
+        for (int j = 0; j < L; j++) { cr[j] = 0.0f; ar[j] = 0.0f; }
         float c = 0.0f;
         uint32_t acc = 0;   // pending output bits (low nacc bits), still as SIGN bits (inverted at store)
         int nacc = 0;       // warp-uniform
         int wi = 0;
+        uint32_t ow0 = 0, ow1 = 0, ow2 = 0;  // the last words of the current 16-byte output group
+        uint4* const out4 = reinterpret_cast<uint4*>(plane_out + b * wpb);
+        // one 16-byte store per 4 words: 4x fewer L1 wavefronts than word stores (each lane hits its own line)
+        auto put = [&](uint32_t o) {
+            if ((wi & 3) == 3) {
+                if (live && wi < wpb) out4[wi >> 2] = make_uint4(~ow0, ~ow1, ~ow2, ~o);
+            }
+            ow0 = ow1; ow1 = ow2; ow2 = o;
+            wi++;
+        };
 
         for (int t = 0; t < nbody; t++) {
             const int st = t & 1;
             mbar_wait(bar0 + st * 8, (phases >> st) & 1u);
             phases ^= 1u << st;
-            const uint32_t lo = (t < 2) ? lo_lead : lo_main;
+            // LUT column for the pad steps (first kPad steps of body 0) and for the rest of the body
+            const uint32_t lo_a = (t == 0) ? lo_zero : ((t < 2) ? lo_lead : lo_main);
+            const uint32_t lo_b = (t < 2) ? lo_lead : lo_main;
             const uint32_t src = row + st * G::kStageBytes;
             const bool emit = t >= 2;
             uint32_t w = 0;
 
 #pragma unroll
-            for (int g = 0; g < CL / 8; g++) {
+            for (int g = 0; g < L / 8; g++) {
                 const uint4 v = lds128(src + g * 16);
                 const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+                const uint32_t lo = (g * 8 < G::kPad) ? lo_a : lo_b;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
 #pragma unroll
                     for (int s = 0; s < 2; s++) {
                         const int j = g * 8 + q * 2 + s;
+                        const int jo = (j + L - CL) % L;  // the slot written CL steps ago
                         // {byte0: lane*4 (or the zero column), byte1: I or Q, bytes 2-3: LUT base >> 16}
                         const uint32_t ai = __byte_perm(xs[q], lo, s ? 0x7624 : 0x7604);
                         const uint32_t aq = __byte_perm(xs[q], lo, s ? 0x7634 : 0x7614);
                         const float m = __fadd_rn(lds_f32(ai), lds_f32(aq));   // decode.go:222
                         c = __fadd_rn(c, m);                                   // csum[k+1], decode.go:234
-                        const float a = __fsub_rn(c, cr[j]);                   // csum[k+1] - csum[k+1-CL]
-                        cr[j] = c;
-                        const float f = __fsub_rn(ar[j], a);                   // decode.go:242
+                        const float a = __fsub_rn(c, cr[jo]);                  // csum[k+1] - csum[k+1-CL]
+                        cr[j] = c;                                             // slot j died L-CL steps ago
+                        const float f = __fsub_rn(ar[jo], a);                  // decode.go:242
                         ar[j] = a;
                         w = __funnelshift_l(__float_as_uint(f), w, 1);         // sign bit in
                         if ((j & 31) == 31) {
                             // 32 more bits complete: emit one word (acc keeps the nacc pending bits)
                             if (emit) {
-                                const uint32_t o = __funnelshift_r(w, acc, nacc);
-                                if (live && wi < wpb) plane_out[b * wpb + wi] = ~o;
-                                wi++;
+                                put(__funnelshift_r(w, acc, nacc));
                                 acc = w;
                             }
                         }
@@ -236,15 +259,14 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
             issue(t + 2);
 
             if constexpr (G::kTailBits != 0) {
-                // branch-free append of the body's last CL%32 bits (state only advances when emit)
+                // branch-free append of the body's last L%32 bits (state only advances when emit)
                 const uint32_t y = w & ((1u << G::kTailBits) - 1u);
                 const uint32_t hi = acc >> (32 - G::kTailBits);
                 const uint32_t lw = (acc << G::kTailBits) | y;
                 const int n2 = nacc + G::kTailBits;
                 const bool full = emit && n2 >= 32;
                 const uint32_t o = __funnelshift_r(lw, hi, n2 & 31);
-                if (full && live && wi < wpb) plane_out[b * wpb + wi] = ~o;
-                wi += full ? 1 : 0;
+                if (full) put(o);
                 nacc = emit ? (n2 & 31) : nacc;
                 acc = emit ? lw : acc;
             }
@@ -261,9 +283,9 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
 
 template <int CL>
 constexpr int fast_warps() {
-    // registers: 2*CL ring values + ~30 working registers; the register file is handed out in
+    // registers: 2*L ring values + ~40 working registers; the register file is handed out in
     // units that make 8/12/16 warps per SM the useful steps (255/168/128 registers per thread)
-    return (2 * CL + 40 <= 128) ? 16 : ((2 * CL + 40 <= 168) ? 12 : 8);
+    return (2 * fast_body_len(CL) + 40 <= 128) ? 16 : ((2 * fast_body_len(CL) + 40 <= 168) ? 12 : 8);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -295,13 +317,14 @@ int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_sample
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
+    if (2 * G::kRowBytes > 2 * BS || hist_samples < 2 * G::L) return (int)cudaErrorInvalidValue;
     // the IQ bytes of the call as a 2D uint8 tensor: [nblocks rows][BlockSize2 bytes]
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return (int)cudaErrorNotSupported;
     CUtensorMap map;
     const cuuint64_t gdim[2] = {(cuuint64_t)(2 * BS), (cuuint64_t)nblocks};
     const cuuint64_t gstride[1] = {(cuuint64_t)(2 * BS)};
-    const cuuint32_t box[2] = {(cuuint32_t)G::kStrideBytes, 32u};
+    const cuuint32_t box[2] = {(cuuint32_t)G::kRowBytes, 32u};
     const cuuint32_t estr[2] = {1u, 1u};
     CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(iq), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -319,7 +342,7 @@ int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_sample
 }
 
 // chip lengths with a specialised kernel: every value the reference CLI accepts (flags.go:127-132
-// allows 8,32,40,...,96) except 8 (BlockSize 512: rows of 16 bytes are too small to stage);
+// allows 8,32,40,...,96) except 8 (BlockSize 512: a row is too short for two bodies of lead-in);
 // anything else (e.g. 78, the fixture's capture rate) uses the generic kernel.
 inline int demod_fast_variant(int CL, int BS) {
     (void)BS;
@@ -336,8 +359,7 @@ inline int launch_demod_fast(int variant, int warps, const uint8_t* iq, const ui
 #define ERT_FAST_ARGS iq, hist, hist_samples, hist_valid, lut, plane_out, nblocks, BS, tile_counter, st
 #define ERT_FAST_CASE(N) \
     case N: return launch_demod_fast_cw<N, fast_warps<N>()>(ERT_FAST_ARGS);
-    if (variant == 72 && warps == 8) return launch_demod_fast_cw<72, 8>(ERT_FAST_ARGS);
-    if (variant == 72 && warps == 12) return launch_demod_fast_cw<72, 12>(ERT_FAST_ARGS);
+    (void)warps;
     switch (variant) {
         ERT_FAST_CASE(32) ERT_FAST_CASE(40) ERT_FAST_CASE(48) ERT_FAST_CASE(56) ERT_FAST_CASE(64)
         ERT_FAST_CASE(72) ERT_FAST_CASE(80) ERT_FAST_CASE(88) ERT_FAST_CASE(96)

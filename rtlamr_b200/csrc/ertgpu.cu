@@ -451,7 +451,7 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
     d.PS = c.preamble_symbols; d.PK = c.packet_symbols;
     d.PL = c.preamble_length; d.PKL = c.packet_length; d.BUF = c.buffer_length;
     d.words_per_block = d.BS / 32;
-    d.hist_words = (d.PKL + 31) / 32;
+    d.hist_words = ((d.PKL + 31) / 32 + 3) & ~3;  // multiple of 4: the call's first word is 16-byte aligned
     d.hist_samples = d.PKL;
     d.packet_bytes = c.packet_bytes;
     d.nproto = (int32_t)h->protos.size();

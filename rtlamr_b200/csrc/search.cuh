@@ -34,7 +34,7 @@ constexpr int kSearchThreads = 256;
 constexpr int kSearchTile = 2048;   // words of starts per CTA iteration
 constexpr int kSearchProbe = 12;    // preamble bits tested unconditionally
 constexpr int kSearchMaxPre = 4;
-constexpr int kSearchMaxHalo = 160; // words: (31*SL + 31)/32 + 2 for SL <= 160
+constexpr int kSearchMaxHalo = 168; // words: (127 + 31*SL)/32 + 2 for SL <= 160
 
 struct SearchParams {
     int32_t offb[ERTGPU_MAX_PREAMBLE];              // 4 * ((sh0 + k*SL) >> 5): byte offset of the window's first word
@@ -52,7 +52,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     return v;
 }
 
-// The plane's first start lies in word 0 (p0 < 32), so tile t starts at plane word t*kSearchTile:
+// The plane's first start lies in the first 4 words (p0 < 128), so tile t starts at plane word t*kSearchTile:
 // 16-byte aligned, fetched with one cp.async.bulk per tile into a 2-stage ring (the plane is
 // allocated with kSearchTile + kSearchMaxHalo words of slack so the last tile can over-read).
 template <int NPRE>
@@ -130,7 +130,7 @@ search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __res
 
 // host: fill the launch constants.  p0 = plane bit of start 0 (must lie in word 0).
 inline bool make_search_params(const DevCfg& c, long long p0, long long nwords, SearchParams* sp) {
-    if (c.npre > kSearchMaxPre || p0 < 0 || p0 >= 32) return false;
+    if (c.npre > kSearchMaxPre || p0 < 0 || p0 >= 128) return false;
     memset(sp, 0, sizeof(*sp));
     const int sh0 = (int)p0;
     int maxbits = 0;
@@ -147,7 +147,7 @@ inline bool make_search_params(const DevCfg& c, long long p0, long long nwords, 
         sp->shk[k] = (int32_t)(off & 31);
     }
     sp->npre = c.npre;
-    sp->halo_words = (int32_t)(((sh0 + (long long)(maxbits - 1) * c.SL) >> 5) + 2);
+    sp->halo_words = (int32_t)(((sh0 + (long long)(maxbits - 1) * c.SL) >> 5) + 2);  // sh0 < 128 covers word0
     if (sp->halo_words > kSearchMaxHalo) return false;
     sp->nwords = nwords;
     return true;
