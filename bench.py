@@ -56,7 +56,9 @@ def parse_args():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every
+    ~2 ms from a thread (the timed region of a default run is only a few ms long), with the
+    `nvidia-smi -lms` recipe as fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -64,27 +66,76 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.nvml, self.stop_flag, self.thread = None, False, None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except Exception:
+                return self.gpu
+        return self.gpu
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self._visible_index()}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((time.time(), sm, mx, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0: float, t1: float):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            n = self.nvml
+            rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+            sm = sorted(r[1] for r in rows)
+            bits = 0
+            for r in rows:
+                bits |= r[3]
+            names = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, v in names.items() if bits & v)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": rows[0][2] if rows else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        time.sleep(0.1)
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
-        rows = [r for (t, r) in self.rows if t0 - 0.15 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.05] or [r for (_, r) in self.rows]
         for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
@@ -99,7 +150,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -133,7 +184,8 @@ def cpu_rate(nthreads: int, sample_mib: int, repeats: int = 1):
         t.join()
     dt = time.perf_counter() - t0
     total = nthreads * repeats * (iq.size // 2)
-    return total / dt / 1e6, dt, counts[0], f"first {sample_mib} MiB of the synthetic stream x {nthreads} independent decoders"
+    return total / dt / 1e6, dt, counts[0], (f"first {sample_mib} MiB of the synthetic stream, decoded {repeats}x by each of "
+                                             f"{nthreads} independent decoders")
 
 
 def run_reference(args):
@@ -237,7 +289,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.05)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     demod_ms, launches = [], 0
@@ -311,7 +363,7 @@ def run_b200(args):
                 traffic = None
         cpu = None
         if not args.skip_cpu_baseline and world == 1:
-            v, dt, nmsg, sample = cpu_rate(1, args.cpu_sample_mib * 8)   # ~10-30 s of one core
+            v, dt, nmsg, sample = cpu_rate(1, args.cpu_sample_mib * 4, repeats=12)   # ~10-20 s of one core
             cpu = {"value": round(v, 1), "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": sample + f" ({dt:.1f} s; C restatement of the Go Decoder incl. Search and parsers, Go toolchain absent)"}
         line = {
@@ -328,7 +380,7 @@ def run_b200(args):
                     "api": "ertgpu_decode (C ABI), pinned host input, chunked H2D overlapped with kernels"},
             "gpu_launches": int(launches),
             "stage_ms": stages,
-            "roofline": {"bound": "hbm", "kernel": "demod_fast_kernel<72>", "achieved": round(achieved, 1), "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "demod_fast_kernel<72,8>", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes": "2 B per IQ sample x samples per launch"},
             "clocks": clocks,
