@@ -107,7 +107,7 @@ class ClockSampler:
                 self.rows.append((time.time(), sm, mx, rs))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -376,7 +376,7 @@ def run_b200(args):
                        "l2": "input per step (1 GiB) exceeds the 126 MB L2: no flush needed",
                        "sharding": "contiguous block-aligned shards + halo, no collective on the data path"},
             "pkts_per_s": round(n_pkts / (ms_per_step * 1e-3), 1), "pkts_per_step": n_pkts,
-            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h_bytes),
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": int(d2h_bytes) * world,
                     "api": "ertgpu_decode (C ABI), pinned host input, chunked H2D overlapped with kernels"},
             "gpu_launches": int(launches),
             "stage_ms": stages,

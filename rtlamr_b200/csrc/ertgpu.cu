@@ -54,6 +54,11 @@ struct ertgpu_handle {
     size_t stage_bytes = 0;
     RawHit* d_hits = nullptr;
     uint8_t* d_digits = nullptr;
+    int* d_block_slot = nullptr;      // r900: scratch slot of each block of the call (-1 none)
+    int* d_slot_block = nullptr;
+    unsigned int* d_slot_count = nullptr;
+    float* d_r900_scratch = nullptr;  // [slot][r900_span] running sums
+    int r900_slots = 0, r900_span = 0;
     ertgpu_candidate* d_out = nullptr;
     unsigned long long cand_cap = 0;
     unsigned long long* d_counters = nullptr;  // [0]=hits [1]=out [2]=valid [3]=demod work-tile counter
@@ -164,6 +169,10 @@ void free_device(ertgpu_handle* h) {
     cudaFree(h->d_crc);
     cudaFree(h->d_hits);
     cudaFree(h->d_digits);
+    cudaFree(h->d_block_slot);
+    cudaFree(h->d_slot_block);
+    cudaFree(h->d_slot_count);
+    cudaFree(h->d_r900_scratch);
     cudaFree(h->d_out);
     cudaFree(h->d_counters);
     cudaFree(h->d_tap);
@@ -240,10 +249,23 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     // 3. r900 payload digits for hits of an r900 preamble
     const uint8_t* digits = nullptr;
     if (h->has_r900) {
-        r900_replay_kernel<<<148, 64, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c, h->d_hits,
-                                               h->cand_cap, h->d_counters, h->d_digits);
+        CUDA_TRY(h, cudaMemsetAsync(h->d_block_slot, 0xFF, (size_t)nblocks * sizeof(int), st));
+        CUDA_TRY(h, cudaMemsetAsync(h->d_slot_count, 0, sizeof(unsigned int), st));
+        r900_mark_kernel<<<148, 256, 0, st>>>(c, h->d_hits, h->cand_cap, h->d_counters, h->d_block_slot, h->d_slot_block,
+                                              h->r900_slots, h->d_slot_count);
         CUDA_TRY(h, cudaGetLastError());
-        h->launches++;
+        r900_chain_kernel<<<148 * 2, kR900ChainWarps * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c,
+                                                                   h->d_slot_block, h->r900_slots, h->d_slot_count,
+                                                                   h->r900_span, h->d_r900_scratch);
+        CUDA_TRY(h, cudaGetLastError());
+        r900_digits_kernel<<<148 * 4, 256, 0, st>>>(c, h->d_hits, h->cand_cap, h->d_counters, h->d_block_slot, h->r900_span,
+                                                    h->d_r900_scratch, h->d_digits);
+        CUDA_TRY(h, cudaGetLastError());
+        // blocks that found no scratch slot: exact per-candidate replay
+        r900_replay_kernel<<<148, 64, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c, h->d_hits,
+                                               h->cand_cap, h->d_counters, h->d_block_slot, h->d_digits);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 4;
         digits = h->d_digits;
     }
 
@@ -526,7 +548,17 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
     }
     CUDA_TRY(h, cudaMalloc(&h->d_hits, h->cand_cap * sizeof(RawHit)));
     CUDA_TRY(h, cudaMalloc(&h->d_out, h->cand_cap * sizeof(ertgpu_candidate)));
-    if (h->has_r900) CUDA_TRY(h, cudaMalloc(&h->d_digits, h->cand_cap * ERTGPU_R900_DIGITS));
+    if (h->has_r900) {
+        CUDA_TRY(h, cudaMalloc(&h->d_digits, h->cand_cap * ERTGPU_R900_DIGITS));
+        h->r900_span = d.BS + d.PL - d.SL + 4 * ERTGPU_R900_DIGITS * d.CL + 1;
+        if (h->r900_span > d.BUF + 1) h->r900_span = d.BUF + 1;
+        h->r900_slots = (int)std::min<int64_t>(std::max<int64_t>(16, (96ll << 20) / ((int64_t)h->r900_span * 4)), max_blocks_per_call);
+        if (const char* e = getenv("ERTGPU_R900_SLOTS")) h->r900_slots = std::max(1, atoi(e));  // test hook: force the replay fallback
+        CUDA_TRY(h, cudaMalloc(&h->d_block_slot, (size_t)max_blocks_per_call * sizeof(int)));
+        CUDA_TRY(h, cudaMalloc(&h->d_slot_block, (size_t)h->r900_slots * sizeof(int)));
+        CUDA_TRY(h, cudaMalloc(&h->d_slot_count, sizeof(unsigned int)));
+        CUDA_TRY(h, cudaMalloc(&h->d_r900_scratch, (size_t)h->r900_slots * (size_t)h->r900_span * sizeof(float)));
+    }
     CUDA_TRY(h, cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)));
     CUDA_TRY(h, cudaHostAlloc(&h->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
     h->tap_floats = (size_t)std::max(d.BS + d.SL, d.BUF) * 2 + 16;

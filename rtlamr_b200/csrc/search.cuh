@@ -327,6 +327,102 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, con
     }
 }
 
+// ---- r900 DSP half, once per detecting block ------------------------------------------------
+//
+// The r900 parser restarts its float32 running sum at the start of ITS buffer in every block
+// (r900/r900.go:96-100), i.e. at sample (b+1)*BS - BUF of the block b that detects a candidate, and
+// reads 42 digits at payload + k*4*CL, payload = Idx + PL - SL (r900.go:187-193).  All candidates of
+// one block therefore share one chain, and only its first r900_span = BS + PL - SL + 168*CL + 1 running
+// sums can ever be read.  Three small kernels: (1) give every block that has an r900 hit a scratch
+// slot, (2) one WARP per slot rebuilds the chain -- lanes fetch 32 magnitudes in parallel, lane 0 adds
+// them in the reference's order -- (3) one thread per (hit, digit) evaluates the three 4-chip
+// correlators.  Blocks beyond the scratch capacity fall back to r900_replay_kernel.
+
+__global__ void r900_mark_kernel(DevCfg cfg, const RawHit* __restrict__ hits, unsigned long long hit_cap,
+                                 const unsigned long long* __restrict__ hit_count, int* __restrict__ block_slot,
+                                 int* __restrict__ slot_block, int slot_cap, unsigned int* __restrict__ slot_count) {
+    unsigned long long n = *hit_count;
+    if (n > hit_cap) n = hit_cap;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+        const RawHit h = hits[c];
+        if (!cfg.pre_has_r900[h.preamble_id]) continue;
+        const long long b = (long long)(h.s / (unsigned long long)cfg.BS);
+        if (block_slot[b] != -1) continue;
+        if (atomicCAS(&block_slot[b], -1, -3) == -1) {  // -3: being assigned
+            const unsigned int slot = atomicAdd(slot_count, 1u);
+            if ((int)slot < slot_cap) {
+                slot_block[slot] = (int)b;
+                block_slot[b] = (int)slot;
+            } else {
+                block_slot[b] = -2;  // no scratch left: per-candidate replay
+            }
+        }
+    }
+}
+
+constexpr int kR900ChainWarps = 4;
+
+__global__ void __launch_bounds__(kR900ChainWarps * 32)
+r900_chain_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist, int hist_samples, int hist_valid,
+                  const float* __restrict__ lut_g, DevCfg cfg, const int* __restrict__ slot_block, int slot_cap,
+                  const unsigned int* __restrict__ slot_count, int span, float* __restrict__ scratch) {
+    __shared__ float lut[256];
+    __shared__ __align__(16) float mbuf[kR900ChainWarps][32];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int nslots = *slot_count;
+    if (nslots > (unsigned)slot_cap) nslots = (unsigned)slot_cap;
+    for (unsigned int slot = blockIdx.x * kR900ChainWarps + warp; slot < nslots; slot += gridDim.x * kR900ChainWarps) {
+        const long long b = slot_block[slot];
+        const long long first = (b + 1) * cfg.BS - cfg.BUF;  // sample of the parser's signal[0]
+        float* out = scratch + (size_t)slot * (size_t)span;   // out[i] = csum[i], i in [0, span)
+        float s = 0.0f;
+        if (lane == 0) out[0] = 0.0f;
+        float m_next = mag_at(iq, hist, hist_samples, hist_valid, first + lane, lut);
+        for (int base = 0; base + 1 < span; base += 32) {
+            mbuf[warp][lane] = m_next;
+            // fetch the next 32 magnitudes while lane 0 runs the sequential adds of this group
+            if (base + 32 + 1 < span) m_next = mag_at(iq, hist, hist_samples, hist_valid, first + base + 32 + lane, lut);
+            __syncwarp();
+            if (lane == 0) {
+                float acc = s;
+#pragma unroll
+                for (int k = 0; k < 32; k++) {
+                    acc = __fadd_rn(acc, mbuf[warp][k]);  // strictly left to right, r900.go:97-99
+                    mbuf[warp][k] = acc;
+                }
+                s = acc;
+            }
+            __syncwarp();
+            if (base + lane + 1 < span) out[base + lane + 1] = mbuf[warp][lane];
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void r900_digits_kernel(DevCfg cfg, const RawHit* __restrict__ hits, unsigned long long hit_cap,
+                                   const unsigned long long* __restrict__ hit_count, const int* __restrict__ block_slot,
+                                   int span, const float* __restrict__ scratch, uint8_t* __restrict__ digits) {
+    unsigned long long n = *hit_count;
+    if (n > hit_cap) n = hit_cap;
+    const unsigned long long total = n * ERTGPU_R900_DIGITS;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const unsigned long long c = t / ERTGPU_R900_DIGITS;
+        const int k = (int)(t % ERTGPU_R900_DIGITS);
+        const RawHit h = hits[c];
+        if (!cfg.pre_has_r900[h.preamble_id]) continue;
+        const long long b = (long long)(h.s / (unsigned long long)cfg.BS);
+        const int slot = block_slot[b];
+        if (slot < 0) continue;  // handled by the replay kernel
+        const int idx = (int)(h.s % (unsigned long long)cfg.BS);
+        const float* cs = scratch + (size_t)slot * (size_t)span + (idx + cfg.PL - cfg.SL + 4 * k * cfg.CL);
+        digits[c * ERTGPU_R900_DIGITS + k] = r900_digit(cs[0], cs[cfg.CL], cs[2 * cfg.CL], cs[3 * cfg.CL], cs[4 * cfg.CL]);
+    }
+}
+
 // r900 payload digits for each raw hit of an r900 preamble: exact replay of the parser's own
 // running sum (r900/r900.go:96-100), which restarts at sample (b+1)*BS - BUF of the block b
 // that detects the candidate, up to the last payload correlator window.  One thread per hit;
@@ -335,7 +431,7 @@ __global__ void r900_replay_kernel(const uint8_t* __restrict__ iq, const uint8_t
                                    int hist_samples, int hist_valid, const float* __restrict__ lut_g,
                                    DevCfg cfg, const RawHit* __restrict__ hits, unsigned long long hit_cap,
                                    const unsigned long long* __restrict__ hit_count,
-                                   uint8_t* __restrict__ digits) {
+                                   const int* __restrict__ block_slot, uint8_t* __restrict__ digits) {
     __shared__ float lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
     __syncthreads();
@@ -346,6 +442,7 @@ __global__ void r900_replay_kernel(const uint8_t* __restrict__ iq, const uint8_t
         const RawHit h = hits[c];
         if (!cfg.pre_has_r900[h.preamble_id]) continue;
         const long long b = (long long)(h.s / (unsigned long long)cfg.BS);
+        if (block_slot && block_slot[b] >= 0) continue;      // served by the per-block chain
         const int idx = (int)(h.s % (unsigned long long)cfg.BS);
         const long long first = (b + 1) * cfg.BS - cfg.BUF;  // sample of r900 signal[0]
         const int payload = idx + cfg.PL - cfg.SL;           // r900.go:187

@@ -122,6 +122,24 @@ def test_r900_digits_and_tap(built):
     h.close()
 
 
+def test_r900_scratch_overflow_falls_back_to_replay(built, monkeypatch):
+    """With a single scratch slot most blocks must take the per-candidate replay path: same digits."""
+    mt, cl = "r900", 72
+    iq, pk, truth = synth_stream(mt, cl, 1 << 21, spacing=1 << 18)
+    h = capi.new_decoder(mt, cl)
+    iq = whole_blocks(iq, h.cfg.block_size2)
+    ref = h.decode(iq)
+    monkeypatch.setenv("ERTGPU_R900_SLOTS", "1")
+    h1 = capi.new_decoder(mt, cl)
+    got = h1.decode(iq)
+    assert len(got) == len(ref) > 0
+    for f in ("block", "idx", "check_mask", "r900_digits"):
+        assert np.array_equal(got[f], ref[f]), f
+    assert (ref["check_mask"] != 0).sum() >= 7
+    h.close()
+    h1.close()
+
+
 def test_call_splitting_is_invisible(built):
     """N calls of any sizes == one long stream (history carried in the handle, decode.go:165-166)."""
     mt, cl = "scm,scm+,idm,r900", 72
