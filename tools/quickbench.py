@@ -1,7 +1,7 @@
 """scratch: quick device-resident timing of the decode pipeline (not the contract bench)."""
 import sys, time, os
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rtlamr_b200 import capi, synth
 
 mt = sys.argv[1] if len(sys.argv) > 1 else "scm"
