@@ -166,9 +166,17 @@ class Handle:
     def set_demod_variant(self, variant: int):
         self._check(self._L.ertgpu_set_demod_variant(self._h, variant))
 
+    def _buffer(self, cap):
+        # reused between calls: allocating and zeroing tens of MB per call would dominate small decodes
+        buf = getattr(self, "_outbuf", None)
+        if buf is None or len(buf) < cap:
+            buf = np.empty(cap, dtype=CAND_DTYPE)
+            self._outbuf = buf
+        return buf[:cap]
+
     def _deliver(self, call, cap):
         while True:
-            out = np.zeros(cap, dtype=CAND_DTYPE)
+            out = self._buffer(cap)
             n = C.c_size_t(0)
             rc = call(out.ctypes.data, cap, C.byref(n))
             if rc == ECAPACITY and n.value > cap and "internal" not in (
@@ -177,7 +185,7 @@ class Handle:
                 call = lambda p, c, nn: self._L.ertgpu_fetch(self._h, p, c, nn)  # noqa: E731
                 continue
             self._check(rc)
-            return out[:n.value]
+            return out[:n.value].copy()
 
     def decode(self, iq, flags: int = 0, cap: int = 4096) -> np.ndarray:
         """ertgpu_decode on a HOST buffer (numpy uint8 or an address/size pair)."""

@@ -304,6 +304,12 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     return ERTGPU_OK;
 }
 
+bool cand_less(const ertgpu_candidate& a, const ertgpu_candidate& b) {
+    if (a.block != b.block) return a.block < b.block;
+    if (a.preamble_id != b.preamble_id) return a.preamble_id < b.preamble_id;
+    return a.idx < b.idx;
+}
+
 // Wait for the pending pipeline and read its counters (candidates stay on the device).
 int collect_sync(ertgpu_handle* h) {
     if (!h->pending) return ERTGPU_OK;
@@ -330,14 +336,12 @@ int collect(ertgpu_handle* h) {
         h->results.resize(old + h->uncopied_n);
         CUDA_TRY(h, cudaMemcpy(h->results.data() + old, h->d_out, h->uncopied_n * sizeof(ertgpu_candidate), cudaMemcpyDeviceToHost));
         h->uncopied = false;
+        // Slots are handed out by atomics, so a pipeline's records arrive unordered.  Pipelines of one
+        // call cover ascending, disjoint block ranges: sorting each segment as it arrives (while the next
+        // chunk's H2D copy is in flight) leaves the whole list in (block, preamble, idx) order.
+        std::sort(h->results.begin() + (std::ptrdiff_t)old, h->results.end(), cand_less);
     }
     return ERTGPU_OK;
-}
-
-bool cand_less(const ertgpu_candidate& a, const ertgpu_candidate& b) {
-    if (a.block != b.block) return a.block < b.block;
-    if (a.preamble_id != b.preamble_id) return a.preamble_id < b.preamble_id;
-    return a.idx < b.idx;
 }
 
 int deliver(ertgpu_handle* h, ertgpu_candidate* out, size_t cap, size_t* n_out) {
@@ -346,8 +350,7 @@ int deliver(ertgpu_handle* h, ertgpu_candidate* out, size_t cap, size_t* n_out) 
         return fail(h, ERTGPU_ECAPACITY, "internal candidate capacity %llu exceeded (%llu hits): allocate with a larger max_candidates",
                     h->cand_cap, h->need);
     }
-    std::sort(h->results.begin(), h->results.end(), cand_less);
-    if (n_out) *n_out = h->results.size();
+    if (n_out) *n_out = h->results.size();  // already sorted segment by segment in collect()
     if (h->results.size() > cap) return fail(h, ERTGPU_ECAPACITY, "output array holds %zu candidates, %zu needed", cap, h->results.size());
     if (!h->results.empty() && out) memcpy(out, h->results.data(), h->results.size() * sizeof(ertgpu_candidate));
     return ERTGPU_OK;
@@ -552,7 +555,14 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
         CUDA_TRY(h, cudaMalloc(&h->d_digits, h->cand_cap * ERTGPU_R900_DIGITS));
         h->r900_span = d.BS + d.PL - d.SL + 4 * ERTGPU_R900_DIGITS * d.CL + 1;
         if (h->r900_span > d.BUF + 1) h->r900_span = d.BUF + 1;
-        h->r900_slots = (int)std::min<int64_t>(std::max<int64_t>(16, (96ll << 20) / ((int64_t)h->r900_span * 4)), max_blocks_per_call);
+        // scratch slots: one per block that holds an r900 hit.  Sized for one packet per 16 blocks
+        // (at least 64 slots), at most 1 GiB; blocks beyond that use the per-candidate replay.
+        {
+            const int64_t per_slot = (int64_t)h->r900_span * 4;
+            int64_t want = std::max<int64_t>(64, max_blocks_per_call / 16);
+            want = std::min<int64_t>(want, (1ll << 30) / per_slot);
+            h->r900_slots = (int)std::max<int64_t>(1, std::min<int64_t>(want, max_blocks_per_call));
+        }
         if (const char* e = getenv("ERTGPU_R900_SLOTS")) h->r900_slots = std::max(1, atoi(e));  // test hook: force the replay fallback
         CUDA_TRY(h, cudaMalloc(&h->d_block_slot, (size_t)max_blocks_per_call * sizeof(int)));
         CUDA_TRY(h, cudaMalloc(&h->d_slot_block, (size_t)h->r900_slots * sizeof(int)));
@@ -646,7 +656,9 @@ int ertgpu_decode(ertgpu_handle* h, const uint8_t* iq, size_t nbytes, uint32_t f
     if (nblocks == 0) return deliver(h, out, cap, n_out);
 
     // staging chunks (allocated on first use): H2D of chunk i+1 overlaps the kernels of chunk i
-    const int64_t chunk_blocks = std::min<int64_t>(h->max_blocks, std::max<int64_t>(1, (32ll << 20) / (int64_t)bs2));
+    int64_t chunk_mib = 32;
+    if (const char* e = getenv("ERTGPU_CHUNK_MIB")) chunk_mib = std::max(1, atoi(e));  // tuning knob
+    const int64_t chunk_blocks = std::min<int64_t>(h->max_blocks, std::max<int64_t>(1, (chunk_mib << 20) / (int64_t)bs2));
     if (h->stage_bytes < (size_t)chunk_blocks * bs2) {
         for (int k = 0; k < 2; k++) {
             cudaFree(h->d_stage[k]);

@@ -243,12 +243,20 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, con
         if (have) h = hits[c];
         if (have) {
             const int nchunks = (cfg.PK + 31) >> 5;
-            for (int ch = 0; ch < nchunks; ch++) {
+            constexpr int kMaxChunks = (ERTGPU_MAX_PACKET_BYTES * 8 + 31) / 32;
+            // issue all strided plane reads first (independent loads overlap), then ballot
+            uint32_t bit[kMaxChunks];
+#pragma unroll
+            for (int ch = 0; ch < kMaxChunks; ch++) {
                 const int sym = ch * 32 + lane;
-                uint32_t bit = 0;
-                if (sym < cfg.PK) bit = plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL);
-                const uint32_t v = __brev(__ballot_sync(0xFFFFFFFFu, bit));  // MSB = symbol 32*ch
-                if (lane < 4 && ch * 4 + lane < ERTGPU_MAX_PACKET_BYTES) bytes[ch * 4 + lane] = (uint8_t)(v >> (24 - 8 * lane));
+                bit[ch] = (ch < nchunks && sym < cfg.PK) ? plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL) : 0u;
+            }
+#pragma unroll
+            for (int ch = 0; ch < kMaxChunks; ch++) {
+                if (ch < nchunks) {
+                    const uint32_t v = __brev(__ballot_sync(0xFFFFFFFFu, bit[ch]));  // MSB = symbol 32*ch
+                    if (lane < 4 && ch * 4 + lane < ERTGPU_MAX_PACKET_BYTES) bytes[ch * 4 + lane] = (uint8_t)(v >> (24 - 8 * lane));
+                }
             }
             for (int q = nchunks * 4 + lane; q < ERTGPU_MAX_PACKET_BYTES; q += 32) bytes[q] = 0;
             __syncwarp();
