@@ -359,7 +359,10 @@ inline int launch_demod_fast(int variant, int warps, const uint8_t* iq, const ui
 #define ERT_FAST_ARGS iq, hist, hist_samples, hist_valid, lut, plane_out, nblocks, BS, tile_counter, st
 #define ERT_FAST_CASE(N) \
     case N: return launch_demod_fast_cw<N, fast_warps<N>()>(ERT_FAST_ARGS);
-    (void)warps;
+    // tuning knob (ERTGPU_FAST_WARPS): other resident-warp counts for the headline chip length
+    if (variant == 72 && warps == 7) return launch_demod_fast_cw<72, 7>(ERT_FAST_ARGS);
+    if (variant == 72 && warps == 6) return launch_demod_fast_cw<72, 6>(ERT_FAST_ARGS);
+    if (variant == 72 && warps == 4) return launch_demod_fast_cw<72, 4>(ERT_FAST_ARGS);
     switch (variant) {
         ERT_FAST_CASE(32) ERT_FAST_CASE(40) ERT_FAST_CASE(48) ERT_FAST_CASE(56) ERT_FAST_CASE(64)
         ERT_FAST_CASE(72) ERT_FAST_CASE(80) ERT_FAST_CASE(88) ERT_FAST_CASE(96)
