@@ -107,7 +107,7 @@ struct FastGeom {
 // smem map (byte offsets inside the dynamic segment, computed at run time):
 //   [bars: 2 x 8 B per warp][pad][staging of the first warps ...][LUT at the next 64 KiB boundary]
 //   [staging of the remaining warps ...]
-template <int CL, int WARPS>
+template <int CL, int WARPS, bool HYBRID = false>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __restrict__ iq,
                   const uint8_t* __restrict__ hist, int hist_samples, int hist_valid,
@@ -219,6 +219,13 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
             // LUT column for the pad steps (first kPad steps of body 0) and for the rest of the body
             const uint32_t lo_a = (t == 0) ? lo_zero : ((t < 2) ? lo_lead : lo_main);
             const uint32_t lo_b = (t < 2) ? lo_lead : lo_main;
+            // HYBRID: the Q component is computed instead of looked up: x = (127.5 - q) / 127.5 rounded to
+            // nearest is exactly fma(n, rhi, n * rlo) for all 256 byte values (verified exhaustively with
+            // exact arithmetic, tests/test_oracle.py), then squared -- the two roundings of decode.go:212-213.
+            // Zero-magnitude steps multiply by 0 instead.
+            const float kRhi = __uint_as_float(1006665857u), kRlo = __uint_as_float(2952724223u);
+            const float rh_a = (lo_a == lo_zero) ? 0.0f : kRhi, rl_a = (lo_a == lo_zero) ? 0.0f : kRlo;
+            const float rh_b = (lo_b == lo_zero) ? 0.0f : kRhi, rl_b = (lo_b == lo_zero) ? 0.0f : kRlo;
             const uint32_t src = row + st * G::kStageBytes;
             const bool emit = t >= 2;
             uint32_t w = 0;
@@ -228,6 +235,7 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
                 const uint4 v = lds128(src + g * 16);
                 const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
                 const uint32_t lo = (g * 8 < G::kPad) ? lo_a : lo_b;
+                const float rh = (g * 8 < G::kPad) ? rh_a : rh_b, rl = (g * 8 < G::kPad) ? rl_a : rl_b;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
 #pragma unroll
@@ -236,8 +244,16 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
                         const int jo = (j + L - CL) % L;  // the slot written CL steps ago
                         // {byte0: lane*4 (or the zero column), byte1: I or Q, bytes 2-3: LUT base >> 16}
                         const uint32_t ai = __byte_perm(xs[q], lo, s ? 0x7624 : 0x7604);
-                        const uint32_t aq = __byte_perm(xs[q], lo, s ? 0x7634 : 0x7614);
-                        const float m = __fadd_rn(lds_f32(ai), lds_f32(aq));   // decode.go:222
+                        float lq;
+                        if constexpr (HYBRID) {
+                            const float mq = __uint_as_float(__byte_perm(xs[q], 0x47000000u, s ? 0x7634 : 0x7614));  // 32768 + Q
+                            const float nq = __fsub_rn(32895.5f, mq);                                                // 127.5 - Q, exact
+                            const float xq = __fmaf_rn(nq, rh, __fmul_rn(nq, rl));                                   // fl((127.5-Q)/127.5)
+                            lq = __fmul_rn(xq, xq);
+                        } else {
+                            lq = lds_f32(__byte_perm(xs[q], lo, s ? 0x7634 : 0x7614));
+                        }
+                        const float m = __fadd_rn(lds_f32(ai), lq);            // decode.go:222
                         c = __fadd_rn(c, m);                                   // csum[k+1], decode.go:234
                         const float a = __fsub_rn(c, cr[jo]);                  // csum[k+1] - csum[k+1-CL]
                         cr[j] = c;                                             // slot j died L-CL steps ago
@@ -304,12 +320,12 @@ inline EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-template <int CL, int W>
+template <int CL, int W, bool HYBRID = false>
 int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_samples, int hist_valid,
                          const float* lut, uint32_t* plane_out, long long nblocks, int BS,
                          unsigned long long* tile_counter, cudaStream_t st) {
     using G = FastGeom<CL>;
-    auto kern = demod_fast_kernel<CL, W>;
+    auto kern = demod_fast_kernel<CL, W, HYBRID>;
     const int smem = 227 * 1024;
     static bool configured = false;
     if (!configured) {
@@ -360,6 +376,7 @@ inline int launch_demod_fast(int variant, int warps, const uint8_t* iq, const ui
 #define ERT_FAST_CASE(N) \
     case N: return launch_demod_fast_cw<N, fast_warps<N>()>(ERT_FAST_ARGS);
     // tuning knob (ERTGPU_FAST_WARPS): other resident-warp counts for the headline chip length
+    if (variant == 72 && warps == 108) return launch_demod_fast_cw<72, 8, true>(ERT_FAST_ARGS);  // 100 + W: hybrid magnitude
     if (variant == 72 && warps == 7) return launch_demod_fast_cw<72, 7>(ERT_FAST_ARGS);
     if (variant == 72 && warps == 6) return launch_demod_fast_cw<72, 6>(ERT_FAST_ARGS);
     if (variant == 72 && warps == 4) return launch_demod_fast_cw<72, 4>(ERT_FAST_ARGS);

@@ -14,6 +14,7 @@
 #pragma once
 
 #include <cstring>
+#include <type_traits>
 
 #include "demod_fast.cuh"
 #include "demod_generic.cuh"
@@ -243,21 +244,25 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, con
         if (have) h = hits[c];
         if (have) {
             const int nchunks = (cfg.PK + 31) >> 5;
-            constexpr int kMaxChunks = (ERTGPU_MAX_PACKET_BYTES * 8 + 31) / 32;
-            // issue all strided plane reads first (independent loads overlap), then ballot
-            uint32_t bit[kMaxChunks];
+            // issue all strided plane reads of a group first (independent loads overlap), then ballot
+            auto gather = [&](auto maxc) {
+                constexpr int kMax = decltype(maxc)::value;
+                uint32_t bit[kMax];
 #pragma unroll
-            for (int ch = 0; ch < kMaxChunks; ch++) {
-                const int sym = ch * 32 + lane;
-                bit[ch] = (ch < nchunks && sym < cfg.PK) ? plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL) : 0u;
-            }
-#pragma unroll
-            for (int ch = 0; ch < kMaxChunks; ch++) {
-                if (ch < nchunks) {
-                    const uint32_t v = __brev(__ballot_sync(0xFFFFFFFFu, bit[ch]));  // MSB = symbol 32*ch
-                    if (lane < 4 && ch * 4 + lane < ERTGPU_MAX_PACKET_BYTES) bytes[ch * 4 + lane] = (uint8_t)(v >> (24 - 8 * lane));
+                for (int ch = 0; ch < kMax; ch++) {
+                    const int sym = ch * 32 + lane;
+                    bit[ch] = (ch < nchunks && sym < cfg.PK) ? plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL) : 0u;
                 }
-            }
+#pragma unroll
+                for (int ch = 0; ch < kMax; ch++) {
+                    if (ch < nchunks) {
+                        const uint32_t v = __brev(__ballot_sync(0xFFFFFFFFu, bit[ch]));  // MSB = symbol 32*ch
+                        if (lane < 4 && ch * 4 + lane < ERTGPU_MAX_PACKET_BYTES) bytes[ch * 4 + lane] = (uint8_t)(v >> (24 - 8 * lane));
+                    }
+                }
+            };
+            if (nchunks <= 4) gather(std::integral_constant<int, 4>{});
+            else gather(std::integral_constant<int, (ERTGPU_MAX_PACKET_BYTES * 8 + 31) / 32>{});
             for (int q = nchunks * 4 + lane; q < ERTGPU_MAX_PACKET_BYTES; q += 32) bytes[q] = 0;
             __syncwarp();
             if (lane == 0) {

@@ -95,6 +95,27 @@ def test_synthetic_candidates_match_oracle(built, mt, cl, variant):
     h.close()
 
 
+def test_hybrid_magnitude_variant_is_bit_exact(built, monkeypatch, sample_iq):
+    """demod_fast<72, 8, HYBRID>: Q magnitude computed with two float constants instead of the LUT."""
+    monkeypatch.setenv("ERTGPU_FAST_WARPS", "108")
+    mt, cl = "scm", 72
+    for src in ("synthetic", "sample", "extremes"):
+        if src == "synthetic":
+            iq, _, _ = synth_stream(mt, cl, 1 << 21, spacing=1 << 18)
+        elif src == "sample":
+            iq = sample_iq
+        else:
+            iq = np.random.default_rng(3).integers(0, 256, 1 << 21, dtype=np.uint8)   # every byte value, uniformly
+        o, cands, msgs = oracle_run(mt, cl, iq, oracle.SEARCH_EXACT)
+        h = capi.new_decoder(mt, cl)
+        iqb = whole_blocks(iq, h.cfg.block_size2)
+        got = h.decode(iqb)
+        compare_candidates(h, got, o, cands)
+        last = iqb.size // h.cfg.block_size2 - 1
+        assert np.array_equal(h.tap(capi.TAP_QUANTIZED, last), o.quantized())
+        h.close()
+
+
 def test_r900_digits_and_tap(built):
     mt, cl = "r900", 72
     iq, pk, truth = synth_stream(mt, cl, 1 << 20, spacing=1 << 18)

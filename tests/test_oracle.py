@@ -151,3 +151,32 @@ def test_gf32_syndrome_of_encoded_r900_is_zero():
     bad = bytearray(msg)
     bad[3] ^= 1
     assert oracle.gf32_syndrome(bytes(bad)) != bytes(5)
+
+
+def test_two_constant_reciprocal_reproduces_the_lut_division_exactly():
+    """demod_fast's HYBRID variant computes x = fl((127.5 - v) / 127.5) as fma(n, rhi, fl(n * rlo)).
+    Exhaustive proof over the 256 byte values with exact rational arithmetic (a true single-rounding fma)."""
+    from fractions import Fraction
+
+    def rn32(fr):
+        x = np.float32(float(fr))
+        best = None
+        for d in (-1, 0, 1):
+            c = np.uint32(int(x.view(np.uint32)) + d).view(np.float32)
+            err = abs(Fraction(float(c)) - fr)
+            if best is None or err < best[0] or (err == best[0] and (int(c.view(np.uint32)) & 1) == 0):
+                best = (err, c)
+        return best[1]
+
+    rhi = np.uint32(1006665857).view(np.float32)
+    rlo = np.uint32(2952724223).view(np.float32)
+    lut = oracle.maglut()
+    for v in range(256):
+        m = np.uint32(0x47000000 | (v << 8)).view(np.float32)        # the byte-permuted float 32768 + v
+        assert float(m) == 32768.0 + v
+        n = np.float32(32895.5) - m
+        assert float(n) == 127.5 - v                                   # exact
+        t = rn32(Fraction(float(n)) * Fraction(float(rlo)))
+        x = rn32(Fraction(float(n)) * Fraction(float(rhi)) + Fraction(float(t)))
+        assert x == np.float32(np.float32(127.5 - v) / np.float32(127.5)), v
+        assert np.float32(x * x) == lut[v], v
