@@ -327,11 +327,9 @@ int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_sample
     using G = FastGeom<CL>;
     auto kern = demod_fast_kernel<CL, W, HYBRID>;
     const int smem = 227 * 1024;
-    static bool configured = false;
-    if (!configured) {
+    {   // per device, so set on every launch (handles on several GPUs may live in one process)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
     }
     if (2 * G::kRowBytes > 2 * BS || hist_samples < 2 * G::L) return (int)cudaErrorInvalidValue;
     // the IQ bytes of the call as a 2D uint8 tensor: [nblocks rows][BlockSize2 bytes]

@@ -1,0 +1,55 @@
+// receiver.hpp -- SURVEY.md section 8(f1): file/stream ingest in place of rtl_tcp, plus the receive loop's
+// cross-block message dedup.  Mirrors the parts of rtlamr's main.go Receiver that sit around
+// protocol.Decoder.Decode:
+//   * the block reader (main.go:156-205) -- here it reads K*BlockSize2 bytes per iteration from a file or
+//     stdin into pinned host buffers (ertgpu_host_alloc) instead of one block from a TCP socket;
+//   * the decode loop (main.go:207-294) -- Decode, then the prev/next digest maps that drop a message
+//     already reported for the previous block (main.go:244-260,292).
+// Whole blocks only: a trailing partial block is never decoded (main.go:166-186).
+#pragma once
+
+#include <cstdio>
+#include <functional>
+#include <set>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "protocol.hpp"
+
+namespace receiver {
+
+// protocol.Digest (parse.go:87-101)
+using Digest = std::tuple<std::string, uint8_t, uint32_t, std::vector<uint8_t>>;
+Digest NewDigest(const protocol::Message& m);
+
+struct Stats {
+    int64_t blocks = 0, bytes = 0, messages = 0, duplicates = 0;
+    double seconds = 0;
+};
+
+class Receiver {
+public:
+    // msgtypes: comma list as for -msgtype ("all" = scm,scm+,idm,r900, main.go:67-73)
+    Receiver(const std::string& msgtypes, int chipLength, int device, int64_t blocksPerCall);
+    ~Receiver();
+
+    protocol::Decoder& decoder() { return d_; }
+
+    // Run over a FILE* until EOF.  `emit` is called once per reported message (after dedup when unique).
+    Stats Run(FILE* in, bool unique, const std::function<void(const protocol::Message&)>& emit);
+
+    // The dedup step on one Decode result (messages grouped by ascending Block), exposed for tests.
+    void Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
+                const std::function<void(const protocol::Message&)>& emit, Stats& st);
+
+private:
+    protocol::Decoder d_;
+    int64_t blocks_per_call_;
+    uint8_t* buf_[2] = {nullptr, nullptr};
+    size_t buf_bytes_ = 0;
+    std::set<Digest> prev_;
+    int64_t prev_block_ = -2;
+};
+
+}  // namespace receiver
