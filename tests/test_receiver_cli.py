@@ -32,9 +32,19 @@ def test_streaming_in_small_calls_equals_one_shot(built):
 
 
 def test_cross_block_dedup_matches_main_go_rule(built, tmp_path):
-    mt, cl = "scm,idm", 72
-    iq, pk, truth = synth_stream(mt, cl, 1 << 22, spacing=1 << 15)       # 128 packets: some straddle a block edge
+    from rtlamr_b200 import synth
+    mt, cl = "scm", 72
     o = oracle.Oracle(mt, cl)
+    bs, buf, sl = o.cfg.block_size, o.cfg.buffer_length, o.cfg.symbol_length
+    n = 1 << 21
+    pk, truth = synth.make_packets(mt, cl, n, seed=7, spacing=1 << 18)
+    # move every other packet so that its ~69 matching sample phases straddle a block boundary:
+    # the preamble starts at stream bit S + SL, reported with Idx = (S + SL + BUF) mod BS
+    for i in range(1, len(pk), 2):
+        s0 = int(pk["start_sample"][i])
+        idx = (s0 + sl + buf) % bs
+        pk["start_sample"][i] = s0 + ((bs - 2) - idx)          # Idx of the true start = BS - 2
+    iq = synth.host_fill(0, n, 0x5EED0001, pk)
     iq = whole_blocks(iq, o.cfg.block_size2)
     path = tmp_path / "stream.bin"
     iq.tofile(path)
