@@ -85,3 +85,20 @@ def test_host_generator_is_deterministic_and_shardable(built):
     assert np.array_equal(whole, np.concatenate(parts))
     assert 126.5 < whole.mean() < 128.5
     assert len(truth) == 4
+
+
+def test_go_shim_binds_only_declared_symbols():
+    """The cgo shim cannot be compiled here (no Go toolchain); at least every C.ertgpu_* / C.ERTGPU_* name it
+    uses must exist in include/ertgpu.h, and it must keep decode.go's exported surface."""
+    hdr = open(os.path.join(ROOT, "include", "ertgpu.h")).read()
+    go = open(os.path.join(ROOT, "go", "protocol", "decode_cuda.go")).read()
+    used = set(re.findall(r"\bC\.((?:ertgpu|ERTGPU)_[A-Za-z0-9_]+)", go))
+    assert len(used) >= 12
+    for name in sorted(used):
+        assert re.search(r"\b" + re.escape(name) + r"\b", hdr), f"{name} used by the Go shim but not in ertgpu.h"
+    for exported in ("type PacketConfig struct", "type Decoder struct", "func NewDecoder() Decoder",
+                     "func (d *Decoder) RegisterProtocol(p Parser)", "func (d *Decoder) Allocate()",
+                     "Decode(input []byte) chan Message", "func (d Decoder) Log()", "func NextPowerOf2(v int) int",
+                     "type Demodulator interface", "func NewMagLUT()"):
+        assert exported in go, exported
+    assert go.startswith("//go:build cuda")
