@@ -246,7 +246,7 @@ func (d *Decoder) R900Digits(idx int) ([]byte, bool) {
 	return v, ok
 }
 
-// Tap returns the reference buffer `which` (C.ERTGPU_TAP_*) as it would be after the Decode of
+// Tap returns the reference buffer `which` (an ERTGPU_TAP constant) as it would be after the Decode of
 // `block` (parity checks only).
 func (d *Decoder) Tap(which int, block int64) []byte {
 	var n C.size_t
