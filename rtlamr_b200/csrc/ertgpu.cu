@@ -229,12 +229,17 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
             long long tiles = (nwords + kSearchTile - 1) / kSearchTile;
             unsigned grid = (unsigned)std::min<long long>(tiles, 148 * 4);
             if (grid < 1) grid = 1;
+            const int mode = search_mode(c, p0);
+#define ERT_SEARCH(N, M) search_kernel<N, M><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->cand_cap, h->d_counters)
+#define ERT_SEARCH_N(N) do { if (mode == 1) ERT_SEARCH(N, 1); else if (mode == 2) ERT_SEARCH(N, 2); else ERT_SEARCH(N, 0); } while (0)
             switch (c.npre) {
-                case 1: search_kernel<1><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->cand_cap, h->d_counters); break;
-                case 2: search_kernel<2><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->cand_cap, h->d_counters); break;
-                case 3: search_kernel<3><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->cand_cap, h->d_counters); break;
-                default: search_kernel<4><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->cand_cap, h->d_counters); break;
+                case 1: ERT_SEARCH_N(1); break;
+                case 2: ERT_SEARCH_N(2); break;
+                case 3: ERT_SEARCH_N(3); break;
+                default: ERT_SEARCH_N(4); break;
             }
+#undef ERT_SEARCH_N
+#undef ERT_SEARCH
         } else {
             const int nthr = 256;
             long long blocks = std::min<long long>((nwords + nthr - 1) / nthr, 148 * 16);

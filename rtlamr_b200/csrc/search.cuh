@@ -56,7 +56,10 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 // The plane's first start lies in the first 4 words (p0 < 128), so tile t starts at plane word t*kSearchTile:
 // 16-byte aligned, fetched with one cp.async.bulk per tile into a 2-stage ring (the plane is
 // allocated with kSearchTile + kSearchMaxHalo words of slack so the last tile can over-read).
-template <int NPRE>
+// MODE 0: any geometry.  MODE 1: every window is word aligned (first start in bit 0 of a word and
+// SL % 32 == 0).  MODE 2: SL % 32 == 16: even preamble bits are word aligned, odd ones sit half a word in.
+// Every chip length the reference CLI accepts gives MODE 1 or 2 (SL = 2*CL, CL a multiple of 8).
+template <int NPRE, int MODE>
 __global__ void __launch_bounds__(kSearchThreads)
 search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __restrict__ hits,
               unsigned long long hit_cap, unsigned long long* __restrict__ hit_count) {
@@ -95,7 +98,10 @@ search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __res
 #pragma unroll
             for (int k = 0; k < kSearchProbe; k++) {
                 const uint32_t a = row + (uint32_t)sp.offb[k];
-                const uint32_t x = __funnelshift_l(lds_u32(a + 4), lds_u32(a), sp.shk[k]);
+                uint32_t x;
+                if (MODE == 1 || (MODE == 2 && (k & 1) == 0)) x = lds_u32(a);
+                else if (MODE == 2) x = __byte_perm(lds_u32(a + 4), lds_u32(a), 0x5432);  // 16 bits in
+                else x = __funnelshift_l(lds_u32(a + 4), lds_u32(a), sp.shk[k]);
 #pragma unroll
                 for (int p = 0; p < NPRE; p++) m[p] &= x ^ sp.inv[p][k];
             }
@@ -152,6 +158,14 @@ inline bool make_search_params(const DevCfg& c, long long p0, long long nwords, 
     if (sp->halo_words > kSearchMaxHalo) return false;
     sp->nwords = nwords;
     return true;
+}
+
+// which specialisation of search_kernel fits the geometry
+inline int search_mode(const DevCfg& c, long long p0) {
+    if ((p0 & 31) != 0) return 0;
+    if (c.SL % 32 == 0) return 1;
+    if (c.SL % 32 == 16) return 2;
+    return 0;
 }
 
 // slow path kept for more than kSearchMaxPre preambles or very short preambles
