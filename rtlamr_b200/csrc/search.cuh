@@ -325,9 +325,13 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, con
                 rec->preamble_id = h.preamble_id;
                 rec->check_mask = mask;
                 rec->flags = has_dig ? ERTGPU_CAND_HAS_R900 : 0u;
-                for (int q = 0; q < ERTGPU_R900_DIGITS; q++) rec->r900_digits[q] = has_dig ? dig[q] : 0;
                 rec->pad[0] = rec->pad[1] = 0;
                 want_s[warp] = ((mask || !(flags & ERTGPU_DECODE_ONLY_VALID)) ? 1u : 0u) | (mask ? 2u : 0u);
+            }
+            {   // the digits are copied by all lanes (lane 0 only reads them above)
+                const bool has_dig = r900_digits != nullptr && cfg.pre_has_r900[h.preamble_id];
+                for (int q = lane; q < ERTGPU_R900_DIGITS; q += 32)
+                    rec->r900_digits[q] = has_dig ? r900_digits[c * ERTGPU_R900_DIGITS + q] : (uint8_t)0;
             }
         } else if (lane == 0) {
             want_s[warp] = 0;
