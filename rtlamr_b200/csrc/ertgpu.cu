@@ -44,6 +44,7 @@ struct ertgpu_handle {
 
     float* d_lut = nullptr;
     uint16_t* d_crc = nullptr;
+    uint16_t* d_crc_pos = nullptr;  // per-position CRC tables of every screen
     uint32_t* d_plane[2] = {nullptr, nullptr};
     size_t plane_words = 0;
     int cur_plane = 0;
@@ -167,6 +168,7 @@ void free_device(ertgpu_handle* h) {
     for (int k = 0; k < 5; k++) if (h->ev_stage[k]) cudaEventDestroy(h->ev_stage[k]);
     cudaFree(h->d_lut);
     cudaFree(h->d_crc);
+    cudaFree(h->d_crc_pos);
     cudaFree(h->d_hits);
     cudaFree(h->d_digits);
     cudaFree(h->d_block_slot);
@@ -275,7 +277,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     }
 
     // 4. slice + integrity screens
-    extract_kernel<<<148 * 8, kExtractWarps * 32, 0, st>>>(plane, p0, c, h->d_hits, h->cand_cap, h->d_counters, h->d_crc, h->gf,
+    extract_kernel<<<148 * 8, kExtractWarps * 32, 0, st>>>(plane, p0, c, h->d_hits, h->cand_cap, h->d_counters, h->d_crc, h->d_crc_pos, h->gf,
                                            digits, h->block_counter, flags, h->d_out, h->cand_cap,
                                            h->d_counters + 1, h->d_counters + 2);
     CUDA_TRY(h, cudaGetLastError());
@@ -485,7 +487,7 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
     d.hist_samples = d.PKL;
     d.packet_bytes = c.packet_bytes;
     d.nproto = (int32_t)h->protos.size();
-    std::vector<uint16_t> tables;
+    std::vector<uint16_t> tables, pos_tables;
     h->has_r900 = false;
     for (int i = 0; i < d.nproto; i++) {
         const ertgpu_protocol& p = h->protos[i];
@@ -511,6 +513,28 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
         dp.table = i;
         tables.resize((size_t)(i + 1) * 256);
         make_crc_table(p.crc_poly, tables.data() + (size_t)i * 256);
+        {
+            const uint16_t* tb = tables.data() + (size_t)i * 256;
+            auto add_pos = [&](int n, int32_t* base, int32_t* cnt, uint16_t* k) {
+                *base = (int32_t)(pos_tables.size() / 256);
+                *cnt = n;
+                for (int pp = 0; pp < n; pp++)
+                    for (int v = 0; v < 256; v++) {
+                        uint16_t crc = tb[v];                       // byte v processed with a zero register
+                        for (int z = 0; z < n - 1 - pp; z++) crc = (uint16_t)((crc << 8) ^ tb[crc >> 8]);
+                        pos_tables.push_back(crc);
+                    }
+                uint16_t crc = p.crc_init;                          // CRC(init, n zero bytes)
+                for (int z = 0; z < n; z++) crc = (uint16_t)((crc << 8) ^ tb[crc >> 8]);
+                *k = crc;
+            };
+            if (p.check_kind == ERTGPU_CHECK_CRC16) add_pos(p.crc_to - p.crc_from, &dp.pos_base, &dp.pos_n, &dp.pos_k);
+            if (p.check_kind == ERTGPU_CHECK_IDM) {
+                dp.crc_from = 4;
+                add_pos(88, &dp.pos_base, &dp.pos_n, &dp.pos_k);
+                add_pos(6, &dp.pos2_base, &dp.pos2_n, &dp.pos2_k);
+            }
+        }
         if (p.check_kind == ERTGPU_CHECK_R900) {
             d.pre_has_r900[found] = 1;
             h->has_r900 = true;
@@ -546,6 +570,9 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
     CUDA_TRY(h, cudaMemcpy(h->d_lut, h->h_lut, 256 * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMalloc(&h->d_crc, tables.size() * sizeof(uint16_t)));
     CUDA_TRY(h, cudaMemcpy(h->d_crc, tables.data(), tables.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMalloc(&h->d_crc_pos, std::max<size_t>(pos_tables.size(), 256) * sizeof(uint16_t)));
+    if (!pos_tables.empty())
+        CUDA_TRY(h, cudaMemcpy(h->d_crc_pos, pos_tables.data(), pos_tables.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
 
     h->plane_words = (size_t)d.hist_words + (size_t)max_blocks_per_call * d.words_per_block + kSearchTile + kSearchMaxHalo + 8;
     for (int k = 0; k < 2; k++) {

@@ -225,21 +225,20 @@ constexpr int kExtractWarps = 8;
 
 // One WARP per candidate (grid-stride over warps).  Lane l gathers packet symbols l, l+32, ...
 // (decode.go:363-366: bit p of the packet is stream bit start + p*SL); a ballot turns 32 symbols into
-// 4 packet bytes.  Lane 0 then runs the screens of every parser filed under the candidate's preamble
-// with the CRC tables staged in shared memory, and the 160-byte record is written by all lanes.
+// 4 packet bytes.  The warp then runs the screens of every parser filed under the candidate's preamble
+// (CRC-16 folded in parallel through per-position tables), and the 160-byte record is written by all lanes.
 // If `r900_digits` is non-null it holds, per raw hit, the 42 payload digits computed by
 // r900_replay_kernel.
 __global__ void __launch_bounds__(kExtractWarps * 32)
 extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, const RawHit* __restrict__ hits,
                unsigned long long hit_cap, const unsigned long long* __restrict__ hit_count,
-               const uint16_t* __restrict__ crc_tables, Gf32 gf, const uint8_t* __restrict__ r900_digits,
+               const uint16_t* __restrict__ crc_tables, const uint16_t* __restrict__ crc_pos, Gf32 gf,
+               const uint8_t* __restrict__ r900_digits,
                long long first_block, uint32_t flags, ertgpu_candidate* __restrict__ out,
                unsigned long long out_cap, unsigned long long* __restrict__ out_count,
                unsigned long long* __restrict__ valid_count) {
-    __shared__ uint16_t tbl_s[ERTGPU_MAX_PROTOCOLS * 256];
     __shared__ __align__(16) ertgpu_candidate rec_s[kExtractWarps];
-    for (int i = threadIdx.x; i < cfg.nproto * 256; i += blockDim.x) tbl_s[i] = crc_tables[i];
-    __syncthreads();
+    (void)crc_tables;  // the byte-serial tables are kept for reference; the screens use the per-position tables
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     ertgpu_candidate* rec = &rec_s[warp];
     uint8_t* bytes = rec->bytes;
@@ -284,25 +283,38 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, con
                 // of a zeroed buffer (decode.go:363-366)
                 if (cfg.PK & 7) bytes[cfg.PK >> 3] = (uint8_t)(bytes[cfg.PK >> 3] >> (8 - (cfg.PK & 7)));
                 for (int q = cfg.packet_bytes; q < nchunks * 4 && q < ERTGPU_MAX_PACKET_BYTES; q++) bytes[q] = 0;
-                uint32_t mask = 0;
-                const bool has_dig = r900_digits != nullptr && cfg.pre_has_r900[h.preamble_id];
-                const uint8_t* dig = has_dig ? r900_digits + c * ERTGPU_R900_DIGITS : nullptr;
-                for (int i = 0; i < cfg.nproto; i++) {
-                    const DevProto& pr = cfg.proto[i];
-                    if (pr.preamble_id != h.preamble_id) continue;
-                    bool ok = false;
-                    const uint16_t* tbl = tbl_s + 256 * pr.table;
-                    if (pr.check_kind == ERTGPU_CHECK_NONE) {
-                        ok = true;
-                    } else if (pr.check_kind == ERTGPU_CHECK_CRC16) {
-                        ok = crc16(tbl, pr.crc_init, bytes + pr.crc_from, pr.crc_to - pr.crc_from) == pr.crc_residue;
-                    } else if (pr.check_kind == ERTGPU_CHECK_IDM) {
-                        ok = crc16(tbl, pr.crc_init, bytes + 4, 88) == pr.crc_residue;  // idm.go:77
-                        if (ok) {
-                            uint8_t buf[6] = {bytes[9], bytes[10], bytes[11], bytes[12], bytes[88], bytes[89]};
-                            ok = crc16(tbl, pr.crc_init, buf, 6) == pr.crc_residue;     // idm.go:82-87
-                        }
-                    } else if (pr.check_kind == ERTGPU_CHECK_R900 && dig) {
+            }
+            __syncwarp();
+            // Integrity screens of every parser filed under this preamble.  The table CRC of crc/crc.go:49-55 is
+            // linear over GF(2): CRC(init, M) = CRC(init, 0^n) xor XOR_p T_p[M[p]], T_p[v] = CRC(0, v at position p).
+            // Each lane folds the bytes p = lane, lane+32, ... through the per-position tables and the warp XORs the
+            // partial results: a 88-byte IDM check costs 3 lookups per lane instead of 88 dependent ones.
+            uint32_t mask = 0;
+            const bool has_dig = r900_digits != nullptr && cfg.pre_has_r900[h.preamble_id];
+            const uint8_t* dig = has_dig ? r900_digits + c * ERTGPU_R900_DIGITS : nullptr;
+            for (int i = 0; i < cfg.nproto; i++) {
+                const DevProto& pr = cfg.proto[i];
+                if (pr.preamble_id != h.preamble_id) continue;
+                bool ok = false;
+                if (pr.check_kind == ERTGPU_CHECK_NONE) {
+                    ok = true;
+                } else if (pr.check_kind == ERTGPU_CHECK_CRC16 || pr.check_kind == ERTGPU_CHECK_IDM) {
+                    uint32_t part = 0, part2 = 0;
+                    for (int q = lane; q < pr.pos_n; q += 32)
+                        part ^= crc_pos[(size_t)(pr.pos_base + q) * 256 + bytes[pr.crc_from + q]];
+                    if (pr.check_kind == ERTGPU_CHECK_IDM && lane < 6) {   // Bytes[9:13] + Bytes[88:90], idm.go:82-87
+                        const int bi = lane < 4 ? 9 + lane : 84 + lane;
+                        part2 = crc_pos[(size_t)(pr.pos2_base + lane) * 256 + bytes[bi]];
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        part ^= __shfl_xor_sync(0xFFFFFFFFu, part, d);
+                        part2 ^= __shfl_xor_sync(0xFFFFFFFFu, part2, d);
+                    }
+                    ok = (uint16_t)(part ^ pr.pos_k) == pr.crc_residue;
+                    if (pr.check_kind == ERTGPU_CHECK_IDM) ok = ok && (uint16_t)(part2 ^ pr.pos2_k) == pr.crc_residue;
+                } else if (pr.check_kind == ERTGPU_CHECK_R900 && dig) {
+                    if (lane == 0) {
                         uint8_t msg[31];
                         for (int q = 0; q < 31; q++) msg[q] = 0;
                         ok = true;
@@ -311,15 +323,18 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, con
                             if (sym > 31) ok = false;
                             msg[q < 16 ? q : q + 10] = (uint8_t)sym;    // r900.go:215-216
                         }
-                        for (int s = 0; s < 5 && ok; s++) {             // gf.go:163-169, Syndrome(msg,5,29)
-                            const uint8_t root = gf.exp[(29 + s) % 31];
+                        for (int s2 = 0; s2 < 5 && ok; s2++) {          // gf.go:163-169, Syndrome(msg,5,29)
+                            const uint8_t root = gf.exp[(29 + s2) % 31];
                             uint8_t syn = msg[0];
                             for (int q = 1; q < 31; q++) syn = gf_mul(gf, syn, root) ^ msg[q];
                             if (syn) ok = false;
                         }
                     }
-                    if (ok) mask |= 1u << i;
+                    ok = __shfl_sync(0xFFFFFFFFu, ok ? 1 : 0, 0) != 0;
                 }
+                if (ok) mask |= 1u << i;
+            }
+            if (lane == 0) {
                 rec->block = first_block + (long long)(h.s / (unsigned long long)cfg.BS);
                 rec->idx = (int32_t)(h.s % (unsigned long long)cfg.BS);
                 rec->preamble_id = h.preamble_id;
