@@ -229,7 +229,7 @@ constexpr int kExtractWarps = 8;
 // (CRC-16 folded in parallel through per-position tables), and the 160-byte record is written by all lanes.
 // If `r900_digits` is non-null it holds, per raw hit, the 42 payload digits computed by
 // r900_replay_kernel.
-__global__ void __launch_bounds__(kExtractWarps * 32)
+__global__ void __launch_bounds__(kExtractWarps * 32, 4)
 extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, const RawHit* __restrict__ hits,
                unsigned long long hit_cap, const unsigned long long* __restrict__ hit_count,
                const uint16_t* __restrict__ crc_tables, const uint16_t* __restrict__ crc_pos, Gf32 gf,
@@ -257,6 +257,10 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, con
         if (have) h = hits[c];
         if (have) {
             const int nchunks = (cfg.PK + 31) >> 5;
+            // bit p of the packet is plane bit base + p*SL: 32-bit offsets from the word that holds the start
+            const long long base = p0 + (long long)h.s;
+            const uint32_t* __restrict__ pw = plane + (base >> 5);
+            const uint32_t bit0 = (uint32_t)(base & 31);
             // issue all strided plane reads of a group first (independent loads overlap), then ballot
             auto gather = [&](auto maxc) {
                 constexpr int kMax = decltype(maxc)::value;
@@ -264,13 +268,20 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, con
 #pragma unroll
                 for (int ch = 0; ch < kMax; ch++) {
                     const int sym = ch * 32 + lane;
-                    bit[ch] = (ch < nchunks && sym < cfg.PK) ? plane_bit(plane, p0 + (long long)h.s + (long long)sym * cfg.SL) : 0u;
+                    uint32_t bv = 0;
+                    if (ch < nchunks && sym < cfg.PK) {
+                        const uint32_t rel = bit0 + (uint32_t)sym * (uint32_t)cfg.SL;
+                        bv = (pw[rel >> 5] >> (31u - (rel & 31u))) & 1u;
+                    }
+                    bit[ch] = bv;
                 }
 #pragma unroll
                 for (int ch = 0; ch < kMax; ch++) {
                     if (ch < nchunks) {
                         const uint32_t v = __brev(__ballot_sync(0xFFFFFFFFu, bit[ch]));  // MSB = symbol 32*ch
-                        if (lane < 4 && ch * 4 + lane < ERTGPU_MAX_PACKET_BYTES) bytes[ch * 4 + lane] = (uint8_t)(v >> (24 - 8 * lane));
+                        // bytes[] starts at a 4-byte boundary of the record: one word store per 32 symbols
+                        if (lane == 0 && ch * 4 < ERTGPU_MAX_PACKET_BYTES)
+                            reinterpret_cast<uint32_t*>(bytes)[ch] = __byte_perm(v, 0u, 0x0123);
                     }
                 }
             };
