@@ -437,11 +437,19 @@ r900_chain_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hi
         float* out = scratch + (size_t)slot * (size_t)span;   // out[i] = csum[i], i in [0, span)
         float s = 0.0f;
         if (lane == 0) out[0] = 0.0f;
-        float m_next = mag_at(iq, hist, hist_samples, hist_valid, first + lane, lut);
+        // magnitudes are fetched kR900Ahead groups ahead of the sequential adds (global-load latency)
+        constexpr int kR900Ahead = 4;
+        float mq[kR900Ahead];
+#pragma unroll
+        for (int a = 0; a < kR900Ahead; a++)
+            mq[a] = (a * 32 + 1 < span) ? mag_at(iq, hist, hist_samples, hist_valid, first + a * 32 + lane, lut) : 0.0f;
         for (int base = 0; base + 1 < span; base += 32) {
-            mbuf[warp][lane] = m_next;
-            // fetch the next 32 magnitudes while lane 0 runs the sequential adds of this group
-            if (base + 32 + 1 < span) m_next = mag_at(iq, hist, hist_samples, hist_valid, first + base + 32 + lane, lut);
+            mbuf[warp][lane] = mq[0];
+#pragma unroll
+            for (int a = 0; a + 1 < kR900Ahead; a++) mq[a] = mq[a + 1];
+            mq[kR900Ahead - 1] = (base + kR900Ahead * 32 + 1 < span)
+                                     ? mag_at(iq, hist, hist_samples, hist_valid, first + base + kR900Ahead * 32 + lane, lut)
+                                     : 0.0f;
             __syncwarp();
             if (lane == 0) {
                 float acc = s;
