@@ -101,7 +101,7 @@ struct FastGeom {
     static constexpr int kWarpBytes = 2 * kStageBytes;  // 2-stage ring
     static constexpr int kFullWords = L / 32;           // whole output words per body
     static constexpr int kTailBits = L % 32;
-    static_assert(L % 8 == 0 && (kRowUnits & 1) == 1 && L > CL && kPad % 8 == 0 && kPad < L, "bad body length");
+    static_assert(L % 8 == 0 && (kRowUnits & 1) == 1 && L > CL && kPad >= 0 && kPad < L, "bad body length");
 };
 
 // smem map (byte offsets inside the dynamic segment, computed at run time):
@@ -234,14 +234,15 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
             for (int g = 0; g < L / 8; g++) {
                 const uint4 v = lds128(src + g * 16);
                 const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
-                const uint32_t lo = (g * 8 < G::kPad) ? lo_a : lo_b;
-                const float rh = (g * 8 < G::kPad) ? rh_a : rh_b, rl = (g * 8 < G::kPad) ? rl_a : rl_b;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
 #pragma unroll
                     for (int s = 0; s < 2; s++) {
                         const int j = g * 8 + q * 2 + s;
                         const int jo = (j + L - CL) % L;  // the slot written CL steps ago
+                        // the first kPad steps of body 0 are the alignment pad (compile-time choice per step)
+                        const uint32_t lo = (j < G::kPad) ? lo_a : lo_b;
+                        const float rh = (j < G::kPad) ? rh_a : rh_b, rl = (j < G::kPad) ? rl_a : rl_b;
                         // {byte0: lane*4 (or the zero column), byte1: I or Q, bytes 2-3: LUT base >> 16}
                         const uint32_t ai = __byte_perm(xs[q], lo, s ? 0x7624 : 0x7604);
                         float lq;
@@ -356,12 +357,12 @@ int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_sample
 }
 
 // chip lengths with a specialised kernel: every value the reference CLI accepts (flags.go:127-132
-// allows 8,32,40,...,96) except 8 (BlockSize 512: a row is too short for two bodies of lead-in);
-// anything else (e.g. 78, the fixture's capture rate) uses the generic kernel.
+// allows 8,32,40,...,96) except 8, plus 78, the rate the reference's sample.bin fixture was captured at
+// (nothing in the kernel needs CL to be a multiple of 8: only L is).  Anything else uses the generic kernel.
 inline int demod_fast_variant(int CL, int BS) {
     (void)BS;
     switch (CL) {
-        case 32: case 40: case 48: case 56: case 64: case 72: case 80: case 88: case 96: return CL;
+        case 32: case 40: case 48: case 56: case 64: case 72: case 78: case 80: case 88: case 96: return CL;
         default: return 0;
     }
 }
@@ -380,7 +381,7 @@ inline int launch_demod_fast(int variant, int warps, const uint8_t* iq, const ui
     if (variant == 72 && warps == 4) return launch_demod_fast_cw<72, 4>(ERT_FAST_ARGS);
     switch (variant) {
         ERT_FAST_CASE(32) ERT_FAST_CASE(40) ERT_FAST_CASE(48) ERT_FAST_CASE(56) ERT_FAST_CASE(64)
-        ERT_FAST_CASE(72) ERT_FAST_CASE(80) ERT_FAST_CASE(88) ERT_FAST_CASE(96)
+        ERT_FAST_CASE(72) ERT_FAST_CASE(78) ERT_FAST_CASE(80) ERT_FAST_CASE(88) ERT_FAST_CASE(96)
         default: return (int)cudaErrorInvalidValue;
     }
 #undef ERT_FAST_CASE

@@ -36,7 +36,8 @@ __device__ __forceinline__ float mag_at(const uint8_t* __restrict__ iq, const ui
         if (-j > hist_valid) return 0.0f;
         p = hist + 2 * ((long long)hist_samples + j);
     }
-    return __fadd_rn(lut[p[0]], lut[p[1]]);
+    const uint32_t iq16 = *reinterpret_cast<const uint16_t*>(p);  // I in the low byte, Q in the high byte (2-byte aligned)
+    return __fadd_rn(lut[iq16 & 0xFFu], lut[iq16 >> 8]);
 }
 
 // grid: ceil(nblocks / blockDim.x) CTAs; dynamic smem: (256 + 2*CL*blockDim.x) floats

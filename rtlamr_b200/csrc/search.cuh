@@ -325,23 +325,29 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, con
                     ok = (uint16_t)(part ^ pr.pos_k) == pr.crc_residue;
                     if (pr.check_kind == ERTGPU_CHECK_IDM) ok = ok && (uint16_t)(part2 ^ pr.pos2_k) == pr.crc_residue;
                 } else if (pr.check_kind == ERTGPU_CHECK_R900 && dig) {
-                    if (lane == 0) {
-                        uint8_t msg[31];
-                        for (int q = 0; q < 31; q++) msg[q] = 0;
-                        ok = true;
-                        for (int q = 0; q < 21 && ok; q++) {            // r900.go:199-207
-                            const int sym = dig[2 * q] * 6 + dig[2 * q + 1];
-                            if (sym > 31) ok = false;
-                            msg[q < 16 ? q : q + 10] = (uint8_t)sym;    // r900.go:215-216
-                        }
-                        for (int s2 = 0; s2 < 5 && ok; s2++) {          // gf.go:163-169, Syndrome(msg,5,29)
-                            const uint8_t root = gf.exp[(29 + s2) % 31];
-                            uint8_t syn = msg[0];
-                            for (int q = 1; q < 31; q++) syn = gf_mul(gf, syn, root) ^ msg[q];
-                            if (syn) ok = false;
+                    // r900.go:199-221 across the warp: lane q holds message symbol q of the 31-symbol RS word
+                    // (16 data symbols, 10 zeros, 5 parity symbols; each symbol = two base-6 digits).  The Horner
+                    // evaluation of gf.go:163-169 at root a^(29+s) equals XOR_q msg[q] * root^(30-q).
+                    int sym = 0;
+                    bool bad = false;
+                    if (lane < 31 && (lane < 16 || lane >= 26)) {
+                        const int k = lane < 16 ? lane : lane - 10;
+                        sym = dig[2 * k] * 6 + dig[2 * k + 1];
+                        bad = sym > 31;
+                    }
+                    ok = __ballot_sync(0xFFFFFFFFu, bad) == 0;
+                    uint32_t synd = 0;  // 5 syndromes x 5 bits packed
+                    if (sym > 0 && sym < 32) {
+                        const int lg = gf.log[sym];
+#pragma unroll
+                        for (int s2 = 0; s2 < 5; s2++) {
+                            const int e = (lg + ((29 + s2) * (30 - lane)) % 31) % 31;
+                            synd |= (uint32_t)gf.exp[e] << (5 * s2);
                         }
                     }
-                    ok = __shfl_sync(0xFFFFFFFFu, ok ? 1 : 0, 0) != 0;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) synd ^= __shfl_xor_sync(0xFFFFFFFFu, synd, d);
+                    ok = ok && synd == 0;
                 }
                 if (ok) mask |= 1u << i;
             }
@@ -452,12 +458,21 @@ r900_chain_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hi
                                      : 0.0f;
             __syncwarp();
             if (lane == 0) {
+                // 32 magnitudes into registers with vector loads, 32 dependent adds, vector stores back
+                float4 v[8];
+                float4* mv = reinterpret_cast<float4*>(&mbuf[warp][0]);
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = mv[k];
                 float acc = s;
 #pragma unroll
-                for (int k = 0; k < 32; k++) {
-                    acc = __fadd_rn(acc, mbuf[warp][k]);  // strictly left to right, r900.go:97-99
-                    mbuf[warp][k] = acc;
+                for (int k = 0; k < 8; k++) {          // strictly left to right, r900.go:97-99
+                    acc = __fadd_rn(acc, v[k].x); v[k].x = acc;
+                    acc = __fadd_rn(acc, v[k].y); v[k].y = acc;
+                    acc = __fadd_rn(acc, v[k].z); v[k].z = acc;
+                    acc = __fadd_rn(acc, v[k].w); v[k].w = acc;
                 }
+#pragma unroll
+                for (int k = 0; k < 8; k++) mv[k] = v[k];
                 s = acc;
             }
             __syncwarp();
