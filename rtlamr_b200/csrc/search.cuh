@@ -203,23 +203,11 @@ search_generic_kernel(const uint32_t* __restrict__ plane, long long p0, long lon
     }
 }
 
-__device__ __forceinline__ uint16_t crc16(const uint16_t* __restrict__ tbl, uint16_t init,
-                                          const uint8_t* data, int n) {
-    uint16_t crc = init;
-    for (int i = 0; i < n; i++) crc = (uint16_t)((crc << 8) ^ tbl[(crc >> 8) ^ data[i]]);  // crc.go:52-54
-    return crc;
-}
-
 // GF(32) log/exp for the r900 syndrome screen (r900/gf/gf.go:20-57 with order 32, poly 37, generator 2)
 struct Gf32 {
     uint8_t exp[62];
     uint8_t log[32];
 };
-
-__device__ __forceinline__ uint8_t gf_mul(const Gf32& g, uint8_t x, uint8_t y) {
-    if (x == 0 || y == 0) return 0;
-    return g.exp[g.log[x] + g.log[y]];
-}
 
 constexpr int kExtractWarps = 8;
 

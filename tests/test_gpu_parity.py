@@ -143,6 +143,34 @@ def test_r900_digits_and_tap(built):
     h.close()
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_random_geometries_and_call_patterns(built, seed):
+    """Chip lengths the CLI would refuse (odd, tiny, large: generic kernel), random protocol sets, random call
+    sizes: candidates must still equal the reference restatement (exact-search mode where SL % 8 != 0)."""
+    rng = np.random.default_rng(100 + seed)
+    cl = int(rng.choice([9, 16, 33, 50, 100, 120, 24, 61]))
+    names = ["scm", "scm+", "idm", "netidm", "r900", "r900bcd"]
+    k = int(rng.integers(1, 4))
+    mt = ",".join(rng.choice(names, size=k, replace=False))
+    n = 1 << 20
+    iq, pk, truth = synth_stream(mt, cl, n, spacing=1 << 18, pkt_seed=seed)
+    o, cands, msgs = oracle_run(mt, cl, iq)
+    h = capi.new_decoder(mt, cl, max_blocks_per_call=64)
+    bs2 = h.cfg.block_size2
+    iq = whole_blocks(iq, bs2)
+    parts, off, nblk = [], 0, iq.size // bs2
+    while off < nblk:
+        m = int(min(nblk - off, rng.integers(1, 100)))
+        parts.append(h.decode(iq[off * bs2:(off + m) * bs2]))
+        off += m
+    got = np.concatenate(parts)
+    compare_candidates(h, got, o, cands)
+    want_valid = {(m.block, m.idx) for m in msgs}
+    have_valid = {(int(r["block"]), int(r["idx"])) for r in got if r["check_mask"]}
+    assert want_valid <= have_valid
+    h.close()
+
+
 def test_r900_scratch_overflow_falls_back_to_replay(built, monkeypatch):
     """With a single scratch slot most blocks must take the per-candidate replay path: same digits."""
     mt, cl = "r900", 72
