@@ -17,6 +17,8 @@ CLI = os.path.join(ROOT, "rtlamr_b200", "ertgpu_decode_file")
 
 
 def run_cli(path, *args):
+    if not os.path.exists(CLI):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "rtlamr_b200", "host")], check=True, stdout=subprocess.DEVNULL)
     out = subprocess.run([CLI, *args, path], capture_output=True, text=True, timeout=300, check=True)
     return [l for l in out.stdout.splitlines() if l.startswith("{")], out.stderr
 
