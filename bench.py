@@ -292,18 +292,19 @@ def run_b200(args):
         time.sleep(0.05)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    demod_ms, launches = [], 0
+    launches = 0
     t_wall0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
-        demod_ms.append(h.last_stage_ms())
         launches += h.last_launches()
     e1.record(stream)
     barrier()
     t_wall1 = time.time()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    stage_mean, stage_n = h.stage_ms_mean()   # CUDA events recorded by the library around each stage, every timed step
+    assert stage_n == args.steps
     h.set_stage_timing(False)
 
     # ---- end to end through the C-ABI call with pinned host memory (H2D inside the timed region)
@@ -350,8 +351,8 @@ def run_b200(args):
             if os.path.exists(p):
                 peaks = json.load(open(p))
         peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-        dm = sum(d["demod"] for d in demod_ms) / len(demod_ms)
-        stages = {k: round(sum(d[k] for d in demod_ms) / len(demod_ms), 4) for k in demod_ms[0]}
+        dm = stage_mean["demod"]
+        stages = {k: round(v, 4) for k, v in stage_mean.items()}
         achieved = 2.0 * nsamples / (dm * 1e-3) / 1e9   # 2 algorithmic bytes per sample
         traffic = None
         tp = os.path.join(ROOT, "profiles", "demod_traffic.json")

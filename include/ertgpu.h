@@ -185,6 +185,8 @@ int64_t ertgpu_last_launches(const ertgpu_handle *h);
  * search, slice+screens (+r900 replay), history carry} of the last pipeline. */
 int ertgpu_set_stage_timing(ertgpu_handle *h, int32_t enable);
 int ertgpu_last_stage_ms(ertgpu_handle *h, float *ms4);
+/* Mean of the same four stage times over every pipeline since timing was enabled. */
+int ertgpu_stage_ms_mean(ertgpu_handle *h, float *ms4, int64_t *n_pipelines);
 
 /* Parity tap: reference buffer `which` as it would be after the Decode of
  * block `block` (absolute index; must lie inside the last decode call).

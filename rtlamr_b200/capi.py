@@ -64,7 +64,7 @@ EXPORTS = [
     "ertgpu_register_protocol", "ertgpu_stock_protocol", "ertgpu_allocate", "ertgpu_get_config",
     "ertgpu_reset", "ertgpu_decode", "ertgpu_decode_device_async", "ertgpu_fetch",
     "ertgpu_last_counts", "ertgpu_last_launches", "ertgpu_set_stage_timing",
-    "ertgpu_last_stage_ms", "ertgpu_tap", "ertgpu_set_demod_variant",
+    "ertgpu_last_stage_ms", "ertgpu_stage_ms_mean", "ertgpu_tap", "ertgpu_set_demod_variant",
     "ertgpu_host_alloc", "ertgpu_host_free", "ertgpu_synth_fill",
 ]
 
@@ -108,6 +108,7 @@ def lib() -> C.CDLL:
     L.ertgpu_tap.argtypes = [vp, i32, i64, vp, sz, C.POINTER(sz)]
     L.ertgpu_set_stage_timing.argtypes = [vp, i32]
     L.ertgpu_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.ertgpu_stage_ms_mean.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i64)]
     L.ertgpu_set_demod_variant.argtypes = [vp, i32]
     L.ertgpu_host_alloc.argtypes = [C.POINTER(vp), sz]
     L.ertgpu_host_free.argtypes = [vp]
@@ -218,6 +219,11 @@ class Handle:
         ms = (C.c_float * 4)()
         self._check(self._L.ertgpu_last_stage_ms(self._h, ms))
         return dict(zip(("demod", "search", "extract", "carry"), [float(x) for x in ms]))
+
+    def stage_ms_mean(self):
+        ms, n = (C.c_float * 4)(), C.c_int64(0)
+        self._check(self._L.ertgpu_stage_ms_mean(self._h, ms, C.byref(n)))
+        return dict(zip(("demod", "search", "extract", "carry"), [float(x) for x in ms])), n.value
 
     def tap(self, which: int, block: int) -> np.ndarray:
         n = C.c_size_t(0)

@@ -91,6 +91,8 @@ struct ertgpu_handle {
     bool stage_timing = false;
     cudaEvent_t ev_stage[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool stage_valid = false;
+    double stage_sum[4] = {0, 0, 0, 0};  // accumulated since ertgpu_set_stage_timing(1)
+    int64_t stage_n = 0;
     std::vector<ertgpu_candidate> results;
 };
 
@@ -331,6 +333,13 @@ int collect_sync(ertgpu_handle* h) {
     }
     h->uncopied_n = std::min(no, h->cand_cap);
     h->uncopied = h->uncopied_n > 0;
+    if (h->stage_valid) {  // the pipeline's events have completed: fold them into the running sums
+        for (int k = 0; k < 4; k++) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, h->ev_stage[k], h->ev_stage[k + 1]) == cudaSuccess) h->stage_sum[k] += ms;
+        }
+        h->stage_n++;
+    }
     return ERTGPU_OK;
 }
 
@@ -804,6 +813,10 @@ int ertgpu_tap(ertgpu_handle* h, int32_t which, int64_t block, void* dst, size_t
 int ertgpu_set_stage_timing(ertgpu_handle* h, int32_t enable) {
     if (!h || !h->allocated) return ERTGPU_EINVAL;
     h->stage_timing = enable != 0;
+    if (enable) {
+        for (int k = 0; k < 4; k++) h->stage_sum[k] = 0;
+        h->stage_n = 0;
+    }
     return ERTGPU_OK;
 }
 
@@ -816,6 +829,18 @@ int ertgpu_last_stage_ms(ertgpu_handle* h, float* ms4) {
     }
     if (!h->stage_valid) return fail(h, ERTGPU_EINVAL, "stage timing was not enabled for the last decode");
     for (int k = 0; k < 4; k++) CUDA_TRY(h, cudaEventElapsedTime(&ms4[k], h->ev_stage[k], h->ev_stage[k + 1]));
+    return ERTGPU_OK;
+}
+
+int ertgpu_stage_ms_mean(ertgpu_handle* h, float* ms4, int64_t* n_pipelines) {
+    if (!h || !h->allocated || !ms4) return ERTGPU_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->pending) {
+        int rc = collect_sync(h);
+        if (rc) return rc;
+    }
+    for (int k = 0; k < 4; k++) ms4[k] = h->stage_n ? (float)(h->stage_sum[k] / (double)h->stage_n) : 0.0f;
+    if (n_pipelines) *n_pipelines = h->stage_n;
     return ERTGPU_OK;
 }
 
