@@ -84,6 +84,27 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     return v;
 }
 
+// packed fp32 pairs (sm_100 FADD2): lane-wise IEEE round-to-nearest, no flush-to-zero, so each half is
+// bit-identical to a scalar add.rn.f32
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // body length for a chip length: the smallest L >= CL + 1 with L % 8 == 0 and L / 8 odd
 constexpr int fast_body_len(int CL) {
     int L = ((CL + 1 + 7) / 8) * 8;
@@ -91,29 +112,36 @@ constexpr int fast_body_len(int CL) {
     return L;
 }
 
-template <int CL>
+template <int CL, int STAGES = 2>
 struct FastGeom {
     static constexpr int L = fast_body_len(CL);
     static constexpr int kPad = 2 * L - 2 * CL;        // zero-magnitude steps in front of the lead-in
     static constexpr int kRowBytes = 2 * L;            // one body's IQ bytes per chain
     static constexpr int kRowUnits = kRowBytes / 16;   // odd: conflict-free LDS.128
     static constexpr int kStageBytes = 32 * kRowBytes;
-    static constexpr int kWarpBytes = 2 * kStageBytes;  // 2-stage ring
+    static constexpr int kStages = STAGES;              // bodies in flight per warp (3 measured no faster than 2: the refill is not what the warps wait for)
+    static constexpr int kWarpBytes = kStages * kStageBytes;
     static constexpr int kFullWords = L / 32;           // whole output words per body
     static constexpr int kTailBits = L % 32;
+    // the three non-sequential adds of two neighbouring steps as packed FADD2 (one issue slot for two
+    // IEEE adds); rings longer than 88 run out of registers with the pair constraints and stay scalar
+    static constexpr bool kPacked = (L <= 88);
     static_assert(L % 8 == 0 && (kRowUnits & 1) == 1 && L > CL && kPad >= 0 && kPad < L, "bad body length");
+    static_assert(CL % 2 == 0, "the packed-pair rings need an even chip length");
 };
 
 // smem map (byte offsets inside the dynamic segment, computed at run time):
 //   [bars: 2 x 8 B per warp][pad][staging of the first warps ...][LUT at the next 64 KiB boundary]
 //   [staging of the remaining warps ...]
-template <int CL, int WARPS, bool HYBRID = false>
+// VAR: tuning variants kept for the record (bit 0 = HYBRID magnitude, bit 1 = 3-stage staging ring)
+template <int CL, int WARPS, int VAR = 0>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __restrict__ iq,
                   const uint8_t* __restrict__ hist, int hist_samples, int hist_valid,
                   const float* __restrict__ lut_g, uint32_t* __restrict__ plane_out, long long nblocks, int BS,
                   unsigned long long* __restrict__ tile_counter) {
-    using G = FastGeom<CL>;
+    constexpr bool HYBRID = (VAR & 1) != 0;
+    using G = FastGeom<CL, (VAR & 2) ? 3 : 2>;
     constexpr int L = G::L;
     extern __shared__ __align__(128) uint8_t fast_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -124,7 +152,13 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
     const int nbelow = (int)((lut_base - below0) / G::kWarpBytes);
     const uint32_t stage0 = (warp < nbelow) ? below0 + warp * G::kWarpBytes
                                             : lut_base + kLutBytes + (warp - nbelow) * G::kWarpBytes;
-    const uint32_t bar0 = sbase + warp * 16;  // two mbarriers per warp
+    const uint32_t bar0 = sbase + warp * 32;  // kStages (<= 4) mbarriers per warp
+    {   // the staging areas must fit the dynamic segment (they do for every instantiated geometry)
+        uint32_t dyn;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        const int nabove = (WARPS > nbelow) ? WARPS - nbelow : 0;
+        if (lut_base + kLutBytes + (uint32_t)nabove * G::kWarpBytes > sbase + dyn) __trap();
+    }
 
     // ---- prologue: LUT [v][lane] + zero column, barriers ----
     for (int i = threadIdx.x; i < 256 * 33; i += WARPS * 32) {
@@ -133,8 +167,8 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_base + v * 256 + l * 4), "f"(x) : "memory");
     }
     if (lane == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8, 1);
+#pragma unroll
+        for (int s = 0; s < G::kStages; s++) mbar_init(bar0 + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -168,15 +202,15 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
         // exception: block 0 takes its lead-in from the history buffer, so that tile uses one 1D bulk
         // copy per lane instead.
         const bool lane_copies = (tile == 0);
-        auto issue = [&](int t) {
+        auto issue = [&](int t, int stage) {
             if (t >= nbody) return;
-            const uint32_t bar = bar0 + (t & 1) * 8;
+            const uint32_t bar = bar0 + stage * 8;
             if (!lane_copies) {
                 if (lane == 0) {
                     mbar_arrive_expect_tx(bar, 32u * G::kRowBytes);
                     const int x = (t < 2) ? 2 * BS - 2 * G::kRowBytes + t * G::kRowBytes : (t - 2) * G::kRowBytes;
                     const int y = (int)(tile * 32) - (t < 2 ? 1 : 0);
-                    tma_load_2d(stage0 + (t & 1) * G::kStageBytes, &iq_map, x, y, bar);
+                    tma_load_2d(stage0 + stage * G::kStageBytes, &iq_map, x, y, bar);
                 }
                 return;
             }
@@ -189,15 +223,14 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
             else src = iq + b * 2ll * BS + off;
             if (lane == 0) mbar_arrive_expect_tx(bar, 32u * (uint32_t)n);
             __syncwarp();
-            bulk_g2s(row + (t & 1) * G::kStageBytes, src, (uint32_t)n, bar);
+            bulk_g2s(row + stage * G::kStageBytes, src, (uint32_t)n, bar);
         };
-        issue(0);
-        issue(1);
+#pragma unroll
+        for (int s = 0; s < G::kStages; s++) issue(s, s);
 
-        float cr[L], ar[L];
+        float cr[L], ar[L];  // rings; (even, odd) neighbours are used as packed pairs
 #pragma unroll
         for (int j = 0; j < L; j++) { cr[j] = 0.0f; ar[j] = 0.0f; }
-        float c = 0.0f;
         uint32_t acc = 0;   // pending output bits (low nacc bits), still as SIGN bits (inverted at store)
         int nacc = 0;       // warp-uniform
         int wi = 0;
@@ -212,8 +245,8 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
             wi++;
         };
 
+        int st = 0;  // stage of body t = t % kStages
         for (int t = 0; t < nbody; t++) {
-            const int st = t & 1;
             mbar_wait(bar0 + st * 8, (phases >> st) & 1u);
             phases ^= 1u << st;
             // LUT column for the pad steps (first kPad steps of body 0) and for the rest of the body
@@ -229,6 +262,7 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
             const uint32_t src = row + st * G::kStageBytes;
             const bool emit = t >= 2;
             uint32_t w = 0;
+            float c = cr[L - 1];  // the running sum = the last slot of the ring
 
 #pragma unroll
             for (int g = 0; g < L / 8; g++) {
@@ -236,44 +270,69 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
                 const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-#pragma unroll
-                    for (int s = 0; s < 2; s++) {
-                        const int j = g * 8 + q * 2 + s;
-                        const int jo = (j + L - CL) % L;  // the slot written CL steps ago
-                        // the first kPad steps of body 0 are the alignment pad (compile-time choice per step)
-                        const uint32_t lo = (j < G::kPad) ? lo_a : lo_b;
-                        const float rh = (j < G::kPad) ? rh_a : rh_b, rl = (j < G::kPad) ? rl_a : rl_b;
-                        // {byte0: lane*4 (or the zero column), byte1: I or Q, bytes 2-3: LUT base >> 16}
-                        const uint32_t ai = __byte_perm(xs[q], lo, s ? 0x7624 : 0x7604);
-                        float lq;
-                        if constexpr (HYBRID) {
-                            const float mq = __uint_as_float(__byte_perm(xs[q], 0x47000000u, s ? 0x7634 : 0x7614));  // 32768 + Q
-                            const float nq = __fsub_rn(32895.5f, mq);                                                // 127.5 - Q, exact
-                            const float xq = __fmaf_rn(nq, rh, __fmul_rn(nq, rl));                                   // fl((127.5-Q)/127.5)
-                            lq = __fmul_rn(xq, xq);
-                        } else {
-                            lq = lds_f32(__byte_perm(xs[q], lo, s ? 0x7634 : 0x7614));
-                        }
-                        const float m = __fadd_rn(lds_f32(ai), lq);            // decode.go:222
-                        c = __fadd_rn(c, m);                                   // csum[k+1], decode.go:234
-                        const float a = __fsub_rn(c, cr[jo]);                  // csum[k+1] - csum[k+1-CL]
-                        cr[j] = c;                                             // slot j died L-CL steps ago
-                        const float f = __fsub_rn(ar[jo], a);                  // decode.go:242
-                        ar[j] = a;
-                        w = __funnelshift_l(__float_as_uint(f), w, 1);         // sign bit in
-                        if ((j & 31) == 31) {
-                            // 32 more bits complete: emit one word (acc keeps the nacc pending bits)
-                            if (emit) {
-                                put(__funnelshift_r(w, acc, nacc));
-                                acc = w;
-                            }
+                    // two samples (I0 Q0 I1 Q1) per 32-bit word.  kPacked: the three non-sequential adds of the
+                    // pair go through FADD2 (add.f32x2: two independent IEEE fp32 adds, one issue slot); only
+                    // the running sum stays scalar.  CL, L and kPad are even, so pairs never straddle.  The
+                    // rings stay scalar arrays (packed at the point of use): 64-bit ring slots make ptxas
+                    // rotate the pairs and pay it back with ~1.5 MOVs per step at the loop edge.
+                    const int j = g * 8 + q * 2;
+                    const int jo = (j + L - CL) % L;  // the slots written CL steps ago
+                    // the first kPad steps of body 0 are the alignment pad (compile-time choice per step)
+                    const uint32_t lo = (j < G::kPad) ? lo_a : lo_b;
+                    const float rh = (j < G::kPad) ? rh_a : rh_b, rl = (j < G::kPad) ? rl_a : rl_b;
+                    // {byte0: lane*4 (or the zero column), byte1: I or Q, bytes 2-3: LUT base >> 16}
+                    const float li0 = lds_f32(__byte_perm(xs[q], lo, 0x7604));
+                    const float li1 = lds_f32(__byte_perm(xs[q], lo, 0x7624));
+                    float lq0, lq1;
+                    if constexpr (HYBRID) {
+                        const float mq0 = __uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7614));  // 32768 + Q
+                        const float mq1 = __uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7634));
+                        const float nq0 = __fsub_rn(32895.5f, mq0), nq1 = __fsub_rn(32895.5f, mq1);  // 127.5 - Q, exact
+                        const float xq0 = __fmaf_rn(nq0, rh, __fmul_rn(nq0, rl));                    // fl((127.5-Q)/127.5)
+                        const float xq1 = __fmaf_rn(nq1, rh, __fmul_rn(nq1, rl));
+                        lq0 = __fmul_rn(xq0, xq0);
+                        lq1 = __fmul_rn(xq1, xq1);
+                    } else {
+                        lq0 = lds_f32(__byte_perm(xs[q], lo, 0x7614));
+                        lq1 = lds_f32(__byte_perm(xs[q], lo, 0x7634));
+                    }
+                    float m0, m1, f0, f1;
+                    if constexpr (G::kPacked) {
+                        unpack2(add2(pack2(li0, li1), pack2(lq0, lq1)), m0, m1);  // decode.go:222
+                    } else {
+                        m0 = __fadd_rn(li0, lq0);
+                        m1 = __fadd_rn(li1, lq1);
+                    }
+                    const float c0 = __fadd_rn(c, m0);                            // csum[k+1], decode.go:234
+                    c = __fadd_rn(c0, m1);
+                    if constexpr (G::kPacked) {
+                        const uint64_t a = sub2(pack2(c0, c), pack2(cr[jo], cr[jo + 1]));  // csum[k+1] - csum[k+1-CL]
+                        unpack2(sub2(pack2(ar[jo], ar[jo + 1]), a), f0, f1);               // decode.go:242
+                        unpack2(a, ar[j], ar[j + 1]);
+                    } else {
+                        const float a0 = __fsub_rn(c0, cr[jo]), a1 = __fsub_rn(c, cr[jo + 1]);
+                        f0 = __fsub_rn(ar[jo], a0);
+                        f1 = __fsub_rn(ar[jo + 1], a1);
+                        ar[j] = a0;
+                        ar[j + 1] = a1;
+                    }
+                    cr[j] = c0;  // slots j, j+1 died L-CL steps ago
+                    cr[j + 1] = c;
+                    w = __funnelshift_l(__float_as_uint(f0), w, 1);           // sign bits in
+                    w = __funnelshift_l(__float_as_uint(f1), w, 1);
+                    if (((j + 1) & 31) == 31) {
+                        // 32 more bits complete: emit one word (acc keeps the nacc pending bits)
+                        if (emit) {
+                            put(__funnelshift_r(w, acc, nacc));
+                            acc = w;
                         }
                     }
                 }
             }
-            // every lane has read its row of this stage into registers: refill it with body t+2
+            // every lane has read its row of this stage into registers: refill it with body t+kStages
             __syncwarp();
-            issue(t + 2);
+            issue(t + G::kStages, st);
+            st = (st + 1 == G::kStages) ? 0 : st + 1;
 
             if constexpr (G::kTailBits != 0) {
                 // branch-free append of the body's last L%32 bits (state only advances when emit)
@@ -321,12 +380,12 @@ inline EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-template <int CL, int W, bool HYBRID = false>
+template <int CL, int W, int VAR = 0>
 int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_samples, int hist_valid,
                          const float* lut, uint32_t* plane_out, long long nblocks, int BS,
                          unsigned long long* tile_counter, cudaStream_t st) {
-    using G = FastGeom<CL>;
-    auto kern = demod_fast_kernel<CL, W, HYBRID>;
+    using G = FastGeom<CL, (VAR & 2) ? 3 : 2>;
+    auto kern = demod_fast_kernel<CL, W, VAR>;
     const int smem = 227 * 1024;
     {   // per device, so set on every launch (handles on several GPUs may live in one process)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -372,11 +431,29 @@ inline int launch_demod_fast(int variant, int warps, const uint8_t* iq, const ui
                              int hist_valid, const float* lut, uint32_t* plane_out, long long nblocks,
                              int BS, unsigned long long* tile_counter, cudaStream_t st) {
 #define ERT_FAST_ARGS iq, hist, hist_samples, hist_valid, lut, plane_out, nblocks, BS, tile_counter, st
-#define ERT_FAST_CASE(N) \
-    case N: return launch_demod_fast_cw<N, fast_warps<N>()>(ERT_FAST_ARGS);
+    // Work tiles are handed out in rounds of (SMs x resident warps).  With two warps per scheduler the SM's
+    // rate still grows almost linearly with the warp count (measured round time, 7 : 8 warps = 0.93 : 1), so
+    // when 7 warps need no more rounds than 8 (e.g. 4096 tiles of a 1 GiB scm call: 3.95 vs 3.46 rounds, both
+    // end in the 4th) the fuller last round of 7 wins; long calls keep 8.
+    bool seven = false;
+    if (warps == 0) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long T = (nblocks + 31) / 32;
+        const long long r8 = (T + sms * 8 - 1) / (sms * 8), r7 = (T + sms * 7 - 1) / (sms * 7);
+        seven = (double)r7 * 0.93 < (double)r8;
+    }
+#define ERT_FAST_CASE(N)                                                                         \
+    case N:                                                                                      \
+        if constexpr (fast_warps<N>() == 8) {                                                    \
+            if (seven || warps == 7) return launch_demod_fast_cw<N, 7>(ERT_FAST_ARGS);           \
+        }                                                                                        \
+        return launch_demod_fast_cw<N, fast_warps<N>()>(ERT_FAST_ARGS);
     // tuning knob (ERTGPU_FAST_WARPS): other resident-warp counts for the headline chip length
-    if (variant == 72 && warps == 108) return launch_demod_fast_cw<72, 8, true>(ERT_FAST_ARGS);  // 100 + W: hybrid magnitude
-    if (variant == 72 && warps == 7) return launch_demod_fast_cw<72, 7>(ERT_FAST_ARGS);
+    if (variant == 72 && warps == 108) return launch_demod_fast_cw<72, 8, 1>(ERT_FAST_ARGS);  // 100 + W: hybrid magnitude
+    if (variant == 72 && warps == 208) return launch_demod_fast_cw<72, 8, 2>(ERT_FAST_ARGS);  // 200 + W: 3-stage ring
+    if (variant == 72 && warps == 8) return launch_demod_fast_cw<72, 8>(ERT_FAST_ARGS);
     if (variant == 72 && warps == 6) return launch_demod_fast_cw<72, 6>(ERT_FAST_ARGS);
     if (variant == 72 && warps == 4) return launch_demod_fast_cw<72, 4>(ERT_FAST_ARGS);
     switch (variant) {
