@@ -72,6 +72,8 @@ struct ertgpu_handle {
     bool has_r900 = false;
     int demod_variant = 0;      // 0 generic, else specialised chip length
     int demod_warps = 0;        // 0 default; tuning override (env ERTGPU_FAST_WARPS)
+    bool search_legacy = false; // env ERTGPU_SEARCH_LEGACY: the per-bit-load Search kernel (kept for chip lengths like 78 and as a cross-check)
+    int sm_count = 148;
 
     // state of the last enqueued pipeline (for fetch and taps)
     bool pending = false;       // a pipeline is enqueued and not yet synchronised
@@ -228,7 +230,45 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     // 2. preamble search over every start position of the call
     {
         SearchParams sp;
-        if (make_search_params(c, p0, nwords, &sp)) {
+        SlideParams sl;
+        if (!h->search_legacy && make_slide_params(c, p0, nwords, &sl)) {
+            const int smem = 2 * sl.load_words * 4 + 16;
+            const long long tiles = (nwords + sl.tile_words - 1) / sl.tile_words;
+            int per_sm = (227 * 1024) / (smem + 1024);
+            if (per_sm > 2048 / kSlideThreads) per_sm = 2048 / kSlideThreads;
+            unsigned grid = (unsigned)std::min<long long>(tiles, (long long)h->sm_count * per_sm);
+            if (grid < 1) grid = 1;
+            const bool half = (c.SL % 32) == 16;
+#define ERT_SLIDE_K(K)                                                                                           \
+    do {                                                                                                         \
+        CUDA_TRY(h, cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                 \
+        K<<<grid, kSlideThreads, smem, st>>>(plane, sl, h->d_hits, h->cand_cap, h->d_counters);                  \
+    } while (0)
+#define ERT_SLIDE(N, ...)                                                                    \
+    do {                                                                                     \
+        if (half) ERT_SLIDE_K((search_slide_kernel<N, true, ##__VA_ARGS__>));                \
+        else ERT_SLIDE_K((search_slide_kernel<N, false, ##__VA_ARGS__>));                    \
+    } while (0)
+            if (c.npre == 1) {
+                // single preamble: the stock protocols' first 16 bits are compile-time constants
+                // (scm 0xF953, scm+ 0x16A3, idm/netidm 0x5555, r900 0x0000), anything else runs the generic probe
+                switch (slide_pattern(c, 0)) {
+                    case 0xF953u: ERT_SLIDE(1, 0xF953u); break;
+                    case 0x16A3u: ERT_SLIDE(1, 0x16A3u); break;
+                    case 0x5555u: ERT_SLIDE(1, 0x5555u); break;
+                    case 0x0000u: ERT_SLIDE(1, 0x0000u); break;
+                    default: ERT_SLIDE(1); break;
+                }
+            } else if (c.npre == 2) {
+                ERT_SLIDE(2);
+            } else if (c.npre == 3) {
+                ERT_SLIDE(3);
+            } else {
+                ERT_SLIDE(4);
+            }
+#undef ERT_SLIDE
+#undef ERT_SLIDE_K
+        } else if (make_search_params(c, p0, nwords, &sp)) {
             const size_t smem = 0;
             long long tiles = (nwords + kSearchTile - 1) / kSearchTile;
             unsigned grid = (unsigned)std::min<long long>(tiles, 148 * 4);
@@ -583,7 +623,7 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
     if (!pos_tables.empty())
         CUDA_TRY(h, cudaMemcpy(h->d_crc_pos, pos_tables.data(), pos_tables.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
 
-    h->plane_words = (size_t)d.hist_words + (size_t)max_blocks_per_call * d.words_per_block + kSearchTile + kSearchMaxHalo + 8;
+    h->plane_words = (size_t)d.hist_words + (size_t)max_blocks_per_call * d.words_per_block + kSearchTile + kSearchMaxHalo + kSlideMaxLoad + 8;
     for (int k = 0; k < 2; k++) {
         CUDA_TRY(h, cudaMalloc(&h->d_plane[k], h->plane_words * sizeof(uint32_t)));
         CUDA_TRY(h, cudaMemset(h->d_plane[k], 0, h->plane_words * sizeof(uint32_t)));
@@ -617,6 +657,9 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
 
     h->demod_variant = demod_fast_variant(d.CL, d.BS);
     if (const char* e = getenv("ERTGPU_FAST_WARPS")) h->demod_warps = atoi(e);
+    if (const char* e = getenv("ERTGPU_SEARCH_LEGACY")) h->search_legacy = atoi(e) != 0;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    if (h->sm_count < 1) h->sm_count = 148;
     h->cur_plane = h->cur_hist = 0;
     h->hist_valid = 0;
     h->block_counter = 0;

@@ -135,6 +135,196 @@ search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __res
     }
 }
 
+// ---- sliding-window Search (every stock geometry: SL % 16 == 0, first start word aligned) ----
+//
+// Two preamble bits are SL/16 = q whole words apart, so for the chain of start words j, j+q, j+2q, ...
+// the window of bit k+2 at step i is the window of bit k at step i+1.  A thread walks kSlideSeg steps
+// of one chain with the windows of the even bits (E) and of the odd bits (O: q/2 words further on, half
+// a word in when SL % 32 == 16) in registers: a step costs 2-3 LDS for the two NEW windows plus one LOP3
+// per probed bit, instead of one or two LDS per bit.  The first 16 bits are probed this way (2^-16 of the
+// starts survive on noise); the rare word with a live start finishes its bits from shared memory in
+// slide_finish, one copy of cold code outside the unrolled loop.
+//
+// Thread c = c_hi * q + c_lo owns residue c_lo, segment c_hi: start word c_lo + q * (33 * c_hi + i).
+// 33 steps per segment (= 1 mod 32) make the 32 lanes of a warp read 32 consecutive banks at every
+// step, whatever q is; 33 = 3 x 11 lets the registers be a ring of 11 with compile-time indices.
+constexpr int kSlideSeg = 33;    // steps per thread per tile
+constexpr int kSlideRing = 11;   // register ring per parity (unroll factor)
+constexpr int kSlideProbe = 16;  // preamble bits probed from the rings
+constexpr int kSlideWin = kSlideProbe / 2;  // windows kept per parity
+constexpr int kSlideThreads = 256;  // q * nseg of them work: 252 for SL = 144 (smaller CTAs leave more lanes idle)
+constexpr uint32_t kSlideRuntimePat = 0xFFFFFFFFu;
+constexpr int kSlideMaxLoad = 8448 + 200;  // words per stage: the largest tile (q = 4, 8) + the largest halo (q = 12)
+
+struct SlideParams {
+    uint32_t inv[kSearchMaxPre][ERTGPU_MAX_PREAMBLE];  // 0 where P[k]=1, ~0 where P[k]=0
+    int32_t nbits[kSearchMaxPre];
+    int32_t q;           // SL / 16: words between the windows of bits k and k+2
+    int32_t odd_off;     // SL >> 5: word offset of the odd bits' window
+    int32_t half;        // 16 when SL % 32 == 16, else 0: bit shift of the odd bits' window
+    int32_t nseg;        // segments per residue; q * nseg threads work
+    int32_t tile_words;  // q * kSlideSeg * nseg, a multiple of 4
+    int32_t load_words;  // tile + halo, a multiple of 4
+    int32_t w0;          // plane word of start 0 (p0 >> 5)
+    long long nwords;    // words of starts
+};
+
+// A word of starts that survived the probe: test bits kSlideProbe .. nbits-1 from shared memory and emit.
+// wa = shared address of the word's bit-0 window, gw = call-relative word of starts.
+__device__ __noinline__ void slide_finish(const SlideParams* sp, int p, uint32_t wa, uint32_t m, long long gw,
+                                          RawHit* __restrict__ hits, unsigned long long hit_cap,
+                                          unsigned long long* __restrict__ hit_count) {
+    const int nb = sp->nbits[p];
+    for (int k = kSlideProbe; k < nb && m; k++) {
+        uint32_t a = wa + 4u * (uint32_t)((k >> 1) * sp->q);
+        uint32_t x;
+        if (k & 1) {
+            a += 4u * (uint32_t)sp->odd_off;
+            x = __funnelshift_l(lds_u32(a + 4), lds_u32(a), sp->half);
+        } else {
+            x = lds_u32(a);
+        }
+        m &= x ^ sp->inv[p][k];
+    }
+    if (m == 0 || gw >= sp->nwords) return;
+    // one reservation per word of starts (same-address atomics serialise in L2)
+    unsigned long long slot = atomicAdd(hit_count, (unsigned long long)__popc(m));
+    while (m) {
+        const int lead = __clz(m);  // MSB = first start of the word
+        m &= ~(0x80000000u >> lead);
+        if (slot < hit_cap) {
+            RawHit h;
+            h.s = (unsigned long long)((gw << 5) + lead);
+            h.preamble_id = p;
+            h.pad = 0;
+            hits[slot] = h;
+        }
+        slot++;
+    }
+}
+
+// PAT: the first 16 preamble bits as a compile-time constant (bit 15 = preamble bit 0) for single-preamble
+// launches of the stock protocols: the compiler then folds two bits into each LOP3 (the probe is bound by
+// the half-rate integer pipe); kSlideRuntimePat = any preamble, bits taken from the launch constants.
+template <int NPRE, bool HALF, uint32_t PAT = kSlideRuntimePat>
+__global__ void __launch_bounds__(kSlideThreads)
+search_slide_kernel(const uint32_t* __restrict__ plane, const __grid_constant__ SlideParams sp,
+                    RawHit* __restrict__ hits, unsigned long long hit_cap, unsigned long long* __restrict__ hit_count) {
+    extern __shared__ __align__(128) uint32_t slide_smem[];  // [2][load_words] then two mbarriers
+    const uint32_t buf0 = smem_u32(slide_smem);
+    const uint32_t stage_bytes = (uint32_t)sp.load_words * 4u;
+    const uint32_t bar0 = buf0 + 2u * stage_bytes;
+    const long long ntiles = (sp.nwords + sp.tile_words - 1) / sp.tile_words;
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long tile, int st) {
+        mbar_arrive_expect_tx(bar0 + 8 * st, stage_bytes);
+        bulk_g2s(buf0 + st * stage_bytes, plane + tile * sp.tile_words, stage_bytes, bar0 + 8 * st);
+    };
+    if (threadIdx.x == 0 && blockIdx.x < ntiles) issue(blockIdx.x, 0);
+
+    const int q = sp.q;
+    const bool active = (int)threadIdx.x < q * sp.nseg;
+    const int c_lo = (int)threadIdx.x % q, c_hi = (int)threadIdx.x / q;
+    const int j0 = c_lo + q * kSlideSeg * c_hi;  // first start word of this thread inside a tile
+    const uint32_t step = 4u * (uint32_t)q;
+    const uint32_t odd = 4u * (uint32_t)sp.odd_off;
+
+    uint32_t phases = 0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int st = it & 1;
+        const long long next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) issue(next, st ^ 1);  // that stage was released by the barrier below
+        mbar_wait(bar0 + 8 * st, (phases >> st) & 1u);
+        phases ^= 1u << st;
+        const long long t0 = tile * sp.tile_words;
+        if (active) {
+            // window n of this segment: E[n] = word j0 + w0 + q*n, O[n] = the same + odd_off (+ 16 bits)
+            const uint32_t a0 = buf0 + st * stage_bytes + 4u * (uint32_t)(j0 + sp.w0);
+            uint32_t a = a0;
+            auto load_o = [&](uint32_t addr) -> uint32_t {
+                if (HALF) return __byte_perm(lds_u32(addr + odd + 4), lds_u32(addr + odd), 0x5432);
+                return lds_u32(addr + odd);
+            };
+            uint32_t E[kSlideRing], O[kSlideRing];  // rings with compile-time indices
+#pragma unroll
+            for (int n = 0; n < kSlideWin; n++) {  // one window ahead: a step never waits for its own loads
+                E[n] = lds_u32(a);
+                O[n] = load_o(a);
+                a += step;
+            }
+#pragma unroll 1
+            for (int rep = 0; rep < kSlideSeg / kSlideRing; rep++) {
+#pragma unroll
+                for (int i = 0; i < kSlideRing; i++) {
+                    E[(i + kSlideWin) % kSlideRing] = lds_u32(a);  // the newest window of step i+1
+                    O[(i + kSlideWin) % kSlideRing] = load_o(a);
+                    a += step;
+#pragma unroll
+                    for (int p = 0; p < NPRE; p++) {
+                        uint32_t me = 0xFFFFFFFFu, mo = 0xFFFFFFFFu;  // two chains: half the dependent latency
+#pragma unroll
+                        for (int k = 0; k < kSlideProbe; k += 2) {
+                            const uint32_t e = E[(i + k / 2) % kSlideRing], o = O[(i + k / 2) % kSlideRing];
+                            if constexpr (PAT != kSlideRuntimePat) {
+                                me &= ((PAT >> (15 - k)) & 1u) ? e : ~e;
+                                mo &= ((PAT >> (14 - k)) & 1u) ? o : ~o;
+                            } else {
+                                me &= e ^ sp.inv[p][k];
+                                mo &= o ^ sp.inv[p][k + 1];
+                            }
+                        }
+                        const uint32_t m = me & mo;
+                        if (m != 0) {
+                            const int s = rep * kSlideRing + i;
+                            slide_finish(&sp, p, a0 + (uint32_t)s * step, m, t0 + j0 + (long long)q * s, hits, hit_cap,
+                                         hit_count);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with this stage: it may be refilled next iteration
+    }
+}
+
+// the first 16 bits of preamble p as search_slide_kernel's PAT
+inline uint32_t slide_pattern(const DevCfg& c, int p) {
+    uint32_t v = 0;
+    for (int k = 0; k < 16; k++) v = (v << 1) | (c.pre_bits[p][k] ? 1u : 0u);
+    return v;
+}
+
+// host: launch constants of the sliding-window kernel; false when the geometry does not fit it
+inline bool make_slide_params(const DevCfg& c, long long p0, long long nwords, SlideParams* sp) {
+    if (c.npre > kSearchMaxPre || p0 < 0 || (p0 & 31) != 0 || p0 >= 128) return false;
+    if (c.SL % 16 != 0 || c.SL < 64 || c.SL > 192) return false;
+    memset(sp, 0, sizeof(*sp));
+    for (int p = 0; p < c.npre; p++) {
+        if (c.pre_nbits[p] < 16 || c.pre_nbits[p] > 32) return false;
+        sp->nbits[p] = c.pre_nbits[p];
+        for (int k = 0; k < ERTGPU_MAX_PREAMBLE; k++)
+            sp->inv[p][k] = (k < c.pre_nbits[p]) ? (c.pre_bits[p][k] ? 0u : 0xFFFFFFFFu) : 0u;
+    }
+    sp->q = c.SL / 16;
+    sp->odd_off = c.SL >> 5;
+    sp->half = c.SL % 32;
+    sp->nseg = (kSlideThreads / sp->q) & ~3;  // a multiple of 4 keeps the tile a multiple of 16 bytes
+    sp->tile_words = sp->q * kSlideSeg * sp->nseg;
+    sp->w0 = (int32_t)(p0 >> 5);
+    // the last start word of a tile reaches bit 31's window: 15 strides + the odd offset + 2 words
+    const int halo = sp->q * 15 + sp->odd_off + 2 + sp->w0;  // also covers the one-ahead window loads (8 strides)
+    sp->load_words = (sp->tile_words + halo + 3) & ~3;
+    if (sp->load_words > kSlideMaxLoad) return false;
+    sp->nwords = nwords;
+    return true;
+}
+
 // host: fill the launch constants.  p0 = plane bit of start 0 (must lie in word 0).
 inline bool make_search_params(const DevCfg& c, long long p0, long long nwords, SearchParams* sp) {
     if (c.npre > kSearchMaxPre || p0 < 0 || p0 >= 128) return false;
