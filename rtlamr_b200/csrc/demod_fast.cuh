@@ -34,6 +34,8 @@
 
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "ert_common.cuh"
 
 namespace ert {
@@ -59,6 +61,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
+}
+// non-blocking probe of a phase (acquire on success, like the waiting form)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -200,157 +216,167 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
         // Rows past the end of the call and columns past the end of a row are zero-filled by the TMA
         // unit (the steps that read them produce no output).  The first work tile of a call is the
         // exception: block 0 takes its lead-in from the history buffer, so that tile uses one 1D bulk
-        // copy per lane instead.
-        const bool lane_copies = (tile == 0);
-        auto issue = [&](int t, int stage) {
-            if (t >= nbody) return;
-            const uint32_t bar = bar0 + stage * 8;
-            if (!lane_copies) {
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(bar, 32u * G::kRowBytes);
-                    const int x = (t < 2) ? 2 * BS - 2 * G::kRowBytes + t * G::kRowBytes : (t - 2) * G::kRowBytes;
-                    const int y = (int)(tile * 32) - (t < 2 ? 1 : 0);
-                    tma_load_2d(stage0 + stage * G::kStageBytes, &iq_map, x, y, bar);
-                }
-                return;
-            }
-            // stream byte offset of body t relative to the block start: (t - 2) * 2L
-            const long long off = (long long)(t - 2) * G::kRowBytes;
-            long long n = 2ll * BS - off;  // bytes left in the block
-            if (n > G::kRowBytes) n = G::kRowBytes;
-            const uint8_t* src;
-            if (t < 2 && first) src = have_hist ? hist + 2ll * hist_samples + off : iq;  // off < 0: tail of the history
-            else src = iq + b * 2ll * BS + off;
-            if (lane == 0) mbar_arrive_expect_tx(bar, 32u * (uint32_t)n);
-            __syncwarp();
-            bulk_g2s(row + stage * G::kStageBytes, src, (uint32_t)n, bar);
-        };
-#pragma unroll
-        for (int s = 0; s < G::kStages; s++) issue(s, s);
-
+        // copy per lane instead (its own instantiation of the tile code: the hot loop carries neither
+        // that path nor the lead-in special cases).
         float cr[L], ar[L];  // rings; (even, odd) neighbours are used as packed pairs
 #pragma unroll
         for (int j = 0; j < L; j++) { cr[j] = 0.0f; ar[j] = 0.0f; }
         uint32_t acc = 0;   // pending output bits (low nacc bits), still as SIGN bits (inverted at store)
         int nacc = 0;       // warp-uniform
         int wi = 0;
+        const int wlimit = live ? wpb : 0;   // words this lane may store
         uint32_t ow0 = 0, ow1 = 0, ow2 = 0;  // the last words of the current 16-byte output group
         uint4* const out4 = reinterpret_cast<uint4*>(plane_out + b * wpb);
         // one 16-byte store per 4 words: 4x fewer L1 wavefronts than word stores (each lane hits its own line)
         auto put = [&](uint32_t o) {
-            if ((wi & 3) == 3) {
-                if (live && wi < wpb) out4[wi >> 2] = make_uint4(~ow0, ~ow1, ~ow2, ~o);
-            }
+            if ((wi & 3) == 3 && wi < wlimit) out4[wi >> 2] = make_uint4(~ow0, ~ow1, ~ow2, ~o);
             ow0 = ow1; ow1 = ow2; ow2 = o;
             wi++;
         };
-
         int st = 0;  // stage of body t = t % kStages
-        for (int t = 0; t < nbody; t++) {
-            mbar_wait(bar0 + st * 8, (phases >> st) & 1u);
-            phases ^= 1u << st;
-            // LUT column for the pad steps (first kPad steps of body 0) and for the rest of the body
-            const uint32_t lo_a = (t == 0) ? lo_zero : ((t < 2) ? lo_lead : lo_main);
-            const uint32_t lo_b = (t < 2) ? lo_lead : lo_main;
-            // HYBRID: the Q component is computed instead of looked up: x = (127.5 - q) / 127.5 rounded to
-            // nearest is exactly fma(n, rhi, n * rlo) for all 256 byte values (verified exhaustively with
-            // exact arithmetic, tests/test_oracle.py), then squared -- the two roundings of decode.go:212-213.
-            // Zero-magnitude steps multiply by 0 instead.
-            const float kRhi = __uint_as_float(1006665857u), kRlo = __uint_as_float(2952724223u);
-            const float rh_a = (lo_a == lo_zero) ? 0.0f : kRhi, rl_a = (lo_a == lo_zero) ? 0.0f : kRlo;
-            const float rh_b = (lo_b == lo_zero) ? 0.0f : kRhi, rl_b = (lo_b == lo_zero) ? 0.0f : kRlo;
-            const uint32_t src = row + st * G::kStageBytes;
-            const bool emit = t >= 2;
-            uint32_t w = 0;
-            float c = cr[L - 1];  // the running sum = the last slot of the ring
+        bool ready = false;  // the next body's stage was seen complete
+
+        auto run_tile = [&](auto lc_tag) {
+            constexpr bool kLaneCopies = decltype(lc_tag)::value;
+            auto issue = [&](int t, int stage) {
+                if (t >= nbody) return;
+                const uint32_t bar = bar0 + stage * 8;
+                if constexpr (!kLaneCopies) {
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(bar, 32u * G::kRowBytes);
+                        const int x = (t < 2) ? 2 * BS - 2 * G::kRowBytes + t * G::kRowBytes : (t - 2) * G::kRowBytes;
+                        const int y = (int)(tile * 32) - (t < 2 ? 1 : 0);
+                        tma_load_2d(stage0 + stage * G::kStageBytes, &iq_map, x, y, bar);
+                    }
+                } else {
+                    // stream byte offset of body t relative to the block start: (t - 2) * 2L
+                    const long long off = (long long)(t - 2) * G::kRowBytes;
+                    long long n = 2ll * BS - off;  // bytes left in the block
+                    if (n > G::kRowBytes) n = G::kRowBytes;
+                    const uint8_t* src;
+                    if (t < 2 && first) src = have_hist ? hist + 2ll * hist_samples + off : iq;  // off < 0: tail of the history
+                    else src = iq + b * 2ll * BS + off;
+                    if (lane == 0) mbar_arrive_expect_tx(bar, 32u * (uint32_t)n);
+                    __syncwarp();
+                    bulk_g2s(row + stage * G::kStageBytes, src, (uint32_t)n, bar);
+                }
+            };
+            // PHASE 0: body 0 = alignment pad (zero column) + start of the lead-in; PHASE 1: body 1 = rest of the
+            // lead-in, its last step is f[0]; PHASE 2: the block itself, L output bits per body.
+            auto body = [&](auto phase_tag, int t) {
+                constexpr int PHASE = decltype(phase_tag)::value;
+                // the phase was probed in the middle of the previous body: the wait loop (and the latency of
+                // its first probe) is only paid when the refill really is late
+                if (!ready) mbar_wait(bar0 + st * 8, (phases >> st) & 1u);
+                phases ^= 1u << st;
+                // HYBRID: the Q component is computed instead of looked up: x = (127.5 - q) / 127.5 rounded to
+                // nearest is exactly fma(n, rhi, n * rlo) for all 256 byte values (verified exhaustively with
+                // exact arithmetic, tests/test_oracle.py), then squared -- the two roundings of decode.go:212-213.
+                // Zero-magnitude steps multiply by 0 instead.
+                const float kRhi = __uint_as_float(1006665857u), kRlo = __uint_as_float(2952724223u);
+                const uint32_t lo_b = (PHASE == 2) ? lo_main : lo_lead;
+                const uint32_t lo_a = (PHASE == 0) ? lo_zero : lo_b;  // the first kPad steps of body 0
+                const float rh_a = (lo_a == lo_zero) ? 0.0f : kRhi, rl_a = (lo_a == lo_zero) ? 0.0f : kRlo;
+                const float rh_b = (lo_b == lo_zero) ? 0.0f : kRhi, rl_b = (lo_b == lo_zero) ? 0.0f : kRlo;
+                const uint32_t src = row + st * G::kStageBytes;
+                uint32_t w = 0;
+                float c = cr[L - 1];  // the running sum = the last slot of the ring
 
 #pragma unroll
-            for (int g = 0; g < L / 8; g++) {
-                const uint4 v = lds128(src + g * 16);
-                const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+                for (int g = 0; g < L / 8; g++) {
+                    const uint4 v = lds128(src + g * 16);
+                    const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+                    if (g == L / 16) {
+                        const int nst = (st + 1 == G::kStages) ? 0 : st + 1;
+                        ready = mbar_test(bar0 + nst * 8, (phases >> nst) & 1u);
+                    }
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    // two samples (I0 Q0 I1 Q1) per 32-bit word.  kPacked: the three non-sequential adds of the
-                    // pair go through FADD2 (add.f32x2: two independent IEEE fp32 adds, one issue slot); only
-                    // the running sum stays scalar.  CL, L and kPad are even, so pairs never straddle.  The
-                    // rings stay scalar arrays (packed at the point of use): 64-bit ring slots make ptxas
-                    // rotate the pairs and pay it back with ~1.5 MOVs per step at the loop edge.
-                    const int j = g * 8 + q * 2;
-                    const int jo = (j + L - CL) % L;  // the slots written CL steps ago
-                    // the first kPad steps of body 0 are the alignment pad (compile-time choice per step)
-                    const uint32_t lo = (j < G::kPad) ? lo_a : lo_b;
-                    const float rh = (j < G::kPad) ? rh_a : rh_b, rl = (j < G::kPad) ? rl_a : rl_b;
-                    // {byte0: lane*4 (or the zero column), byte1: I or Q, bytes 2-3: LUT base >> 16}
-                    const float li0 = lds_f32(__byte_perm(xs[q], lo, 0x7604));
-                    const float li1 = lds_f32(__byte_perm(xs[q], lo, 0x7624));
-                    float lq0, lq1;
-                    if constexpr (HYBRID) {
-                        const float mq0 = __uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7614));  // 32768 + Q
-                        const float mq1 = __uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7634));
-                        const float nq0 = __fsub_rn(32895.5f, mq0), nq1 = __fsub_rn(32895.5f, mq1);  // 127.5 - Q, exact
-                        const float xq0 = __fmaf_rn(nq0, rh, __fmul_rn(nq0, rl));                    // fl((127.5-Q)/127.5)
-                        const float xq1 = __fmaf_rn(nq1, rh, __fmul_rn(nq1, rl));
-                        lq0 = __fmul_rn(xq0, xq0);
-                        lq1 = __fmul_rn(xq1, xq1);
-                    } else {
-                        lq0 = lds_f32(__byte_perm(xs[q], lo, 0x7614));
-                        lq1 = lds_f32(__byte_perm(xs[q], lo, 0x7634));
-                    }
-                    float m0, m1, f0, f1;
-                    if constexpr (G::kPacked) {
-                        unpack2(add2(pack2(li0, li1), pack2(lq0, lq1)), m0, m1);  // decode.go:222
-                    } else {
-                        m0 = __fadd_rn(li0, lq0);
-                        m1 = __fadd_rn(li1, lq1);
-                    }
-                    const float c0 = __fadd_rn(c, m0);                            // csum[k+1], decode.go:234
-                    c = __fadd_rn(c0, m1);
-                    if constexpr (G::kPacked) {
-                        const uint64_t a = sub2(pack2(c0, c), pack2(cr[jo], cr[jo + 1]));  // csum[k+1] - csum[k+1-CL]
-                        unpack2(sub2(pack2(ar[jo], ar[jo + 1]), a), f0, f1);               // decode.go:242
-                        unpack2(a, ar[j], ar[j + 1]);
-                    } else {
-                        const float a0 = __fsub_rn(c0, cr[jo]), a1 = __fsub_rn(c, cr[jo + 1]);
-                        f0 = __fsub_rn(ar[jo], a0);
-                        f1 = __fsub_rn(ar[jo + 1], a1);
-                        ar[j] = a0;
-                        ar[j + 1] = a1;
-                    }
-                    cr[j] = c0;  // slots j, j+1 died L-CL steps ago
-                    cr[j + 1] = c;
-                    w = __funnelshift_l(__float_as_uint(f0), w, 1);           // sign bits in
-                    w = __funnelshift_l(__float_as_uint(f1), w, 1);
-                    if (((j + 1) & 31) == 31) {
-                        // 32 more bits complete: emit one word (acc keeps the nacc pending bits)
-                        if (emit) {
+                    for (int q = 0; q < 4; q++) {
+                        // two samples (I0 Q0 I1 Q1) per 32-bit word.  kPacked: the three non-sequential adds of the
+                        // pair go through FADD2 (add.f32x2: two independent IEEE fp32 adds, one issue slot); only
+                        // the running sum stays scalar.  CL, L and kPad are even, so pairs never straddle.  The
+                        // rings stay scalar arrays (packed at the point of use): 64-bit ring slots make ptxas
+                        // rotate the pairs and pay it back with ~1.5 MOVs per step at the loop edge.
+                        const int j = g * 8 + q * 2;
+                        const int jo = (j + L - CL) % L;  // the slots written CL steps ago
+                        const uint32_t lo = (j < G::kPad) ? lo_a : lo_b;
+                        const float rh = (j < G::kPad) ? rh_a : rh_b, rl = (j < G::kPad) ? rl_a : rl_b;
+                        // {byte0: lane*4 (or the zero column), byte1: I or Q, bytes 2-3: LUT base >> 16}
+                        const float li0 = lds_f32(__byte_perm(xs[q], lo, 0x7604));
+                        const float li1 = lds_f32(__byte_perm(xs[q], lo, 0x7624));
+                        float lq0, lq1;
+                        if constexpr (HYBRID) {
+                            const float mq0 = __uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7614));  // 32768 + Q
+                            const float mq1 = __uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7634));
+                            const float nq0 = __fsub_rn(32895.5f, mq0), nq1 = __fsub_rn(32895.5f, mq1);  // 127.5 - Q, exact
+                            const float xq0 = __fmaf_rn(nq0, rh, __fmul_rn(nq0, rl));                    // fl((127.5-Q)/127.5)
+                            const float xq1 = __fmaf_rn(nq1, rh, __fmul_rn(nq1, rl));
+                            lq0 = __fmul_rn(xq0, xq0);
+                            lq1 = __fmul_rn(xq1, xq1);
+                        } else {
+                            lq0 = lds_f32(__byte_perm(xs[q], lo, 0x7614));
+                            lq1 = lds_f32(__byte_perm(xs[q], lo, 0x7634));
+                        }
+                        float m0, m1, f0, f1;
+                        if constexpr (G::kPacked) {
+                            unpack2(add2(pack2(li0, li1), pack2(lq0, lq1)), m0, m1);  // decode.go:222
+                        } else {
+                            m0 = __fadd_rn(li0, lq0);
+                            m1 = __fadd_rn(li1, lq1);
+                        }
+                        const float c0 = __fadd_rn(c, m0);                            // csum[k+1], decode.go:234
+                        c = __fadd_rn(c0, m1);
+                        if constexpr (G::kPacked) {
+                            const uint64_t a = sub2(pack2(c0, c), pack2(cr[jo], cr[jo + 1]));  // csum[k+1] - csum[k+1-CL]
+                            unpack2(sub2(pack2(ar[jo], ar[jo + 1]), a), f0, f1);               // decode.go:242
+                            unpack2(a, ar[j], ar[j + 1]);
+                        } else {
+                            const float a0 = __fsub_rn(c0, cr[jo]), a1 = __fsub_rn(c, cr[jo + 1]);
+                            f0 = __fsub_rn(ar[jo], a0);
+                            f1 = __fsub_rn(ar[jo + 1], a1);
+                            ar[j] = a0;
+                            ar[j + 1] = a1;
+                        }
+                        cr[j] = c0;  // slots j, j+1 died L-CL steps ago
+                        cr[j + 1] = c;
+                        w = __funnelshift_l(__float_as_uint(f0), w, 1);           // sign bits in
+                        w = __funnelshift_l(__float_as_uint(f1), w, 1);
+                        if (((j + 1) & 31) == 31 && PHASE == 2) {
+                            // 32 more bits complete: emit one word (acc keeps the nacc pending bits)
                             put(__funnelshift_r(w, acc, nacc));
                             acc = w;
                         }
                     }
                 }
-            }
-            // every lane has read its row of this stage into registers: refill it with body t+kStages
-            __syncwarp();
-            issue(t + G::kStages, st);
-            st = (st + 1 == G::kStages) ? 0 : st + 1;
+                // every lane has read its row of this stage into registers: refill it with body t+kStages
+                __syncwarp();
+                issue(t + G::kStages, st);
+                st = (st + 1 == G::kStages) ? 0 : st + 1;
 
-            if constexpr (G::kTailBits != 0) {
-                // branch-free append of the body's last L%32 bits (state only advances when emit)
-                const uint32_t y = w & ((1u << G::kTailBits) - 1u);
-                const uint32_t hi = acc >> (32 - G::kTailBits);
-                const uint32_t lw = (acc << G::kTailBits) | y;
-                const int n2 = nacc + G::kTailBits;
-                const bool full = emit && n2 >= 32;
-                const uint32_t o = __funnelshift_r(lw, hi, n2 & 31);
-                if (full) put(o);
-                nacc = emit ? (n2 & 31) : nacc;
-                acc = emit ? lw : acc;
-            }
-            if (t == 1) {  // body 1 contributes only its last step = f[0]
-                acc = w & 1u;
-                nacc = 1;
-            }
-        }
+                if constexpr (G::kTailBits != 0 && PHASE == 2) {
+                    // append the body's last L%32 bits
+                    const uint32_t y = w & ((1u << G::kTailBits) - 1u);
+                    const uint32_t hi = acc >> (32 - G::kTailBits);
+                    const uint32_t lw = (acc << G::kTailBits) | y;
+                    const int n2 = nacc + G::kTailBits;
+                    if (n2 >= 32) put(__funnelshift_r(lw, hi, n2 & 31));
+                    nacc = n2 & 31;
+                    acc = lw;
+                }
+                if constexpr (PHASE == 1) {  // body 1 contributes only its last step = f[0]
+                    acc = w & 1u;
+                    nacc = 1;
+                }
+            };
+#pragma unroll
+            for (int s = 0; s < G::kStages; s++) issue(s, s);
+            body(std::integral_constant<int, 0>{}, 0);
+            body(std::integral_constant<int, 1>{}, 1);
+#pragma unroll 1
+            for (int t = 2; t < nbody; t++) body(std::integral_constant<int, 2>{}, t);
+        };
+        if (tile == 0) run_tile(std::true_type{});
+        else run_tile(std::false_type{});
         __syncwarp();
     }
 }
@@ -380,13 +406,42 @@ inline EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
+// Shared-space address of the dynamic segment of a kernel without static shared memory (the first KiB
+// of the window is reserved by the system).  Asked from the device once: the demod kernel's map depends
+// on where the 64 KiB-aligned LUT lands, and the launch requests exactly the bytes the map needs so that
+// CTAs of the Search/extract kernels of another call can share the SM.
+__global__ void smem_base_probe_kernel(uint32_t* out) {
+    extern __shared__ __align__(128) uint8_t probe_smem[];
+    *out = smem_u32(probe_smem);
+}
+inline uint32_t dynamic_smem_base() {
+    static uint32_t base = 0;
+    if (base) return base;
+    uint32_t* d = nullptr;
+    uint32_t h = 0;
+    if (cudaMalloc(&d, 4) != cudaSuccess) return 1024;
+    smem_base_probe_kernel<<<1, 1, 1024>>>(d);
+    if (cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost) != cudaSuccess || h == 0) h = 1024;
+    cudaFree(d);
+    base = h;
+    return base;
+}
+
 template <int CL, int W, int VAR = 0>
 int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_samples, int hist_valid,
                          const float* lut, uint32_t* plane_out, long long nblocks, int BS,
                          unsigned long long* tile_counter, cudaStream_t st) {
     using G = FastGeom<CL, (VAR & 2) ? 3 : 2>;
     auto kern = demod_fast_kernel<CL, W, VAR>;
-    const int smem = 227 * 1024;
+    int smem;
+    {   // mirror of the kernel's map: [barriers 1 KiB][staging][LUT at the next 64 KiB boundary][staging]
+        const uint32_t sbase = dynamic_smem_base();
+        const uint32_t lut_base = (sbase + 1024 + 0xFFFFu) & ~0xFFFFu;
+        const int nbelow = (int)((lut_base - (sbase + 1024)) / G::kWarpBytes);
+        const int nabove = W > nbelow ? W - nbelow : 0;
+        smem = (int)(lut_base + kLutBytes + (uint32_t)nabove * G::kWarpBytes - sbase);
+        if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+    }
     {   // per device, so set on every launch (handles on several GPUs may live in one process)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
