@@ -381,7 +381,7 @@ def run_b200(args):
                     "api": "ertgpu_decode (C ABI), pinned host input, chunked H2D overlapped with kernels"},
             "gpu_launches": int(launches),
             "stage_ms": stages,
-            "roofline": {"bound": "hbm", "kernel": "demod_fast_kernel<72,8>", "achieved": round(achieved, 1), "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "demod_fast_kernel<72,W> (W = 7 or 8 resident warps, chosen per call by round count)", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes": "2 B per IQ sample x samples per launch"},
             "clocks": clocks,

@@ -301,6 +301,7 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
                         const int jo = (j + L - CL) % L;  // the slots written CL steps ago
                         const uint32_t lo = (j < G::kPad) ? lo_a : lo_b;
                         const float rh = (j < G::kPad) ? rh_a : rh_b, rl = (j < G::kPad) ? rl_a : rl_b;
+                        (void)rh; (void)rl;
                         // {byte0: lane*4 (or the zero column), byte1: I or Q, bytes 2-3: LUT base >> 16}
                         const float li0 = lds_f32(__byte_perm(xs[q], lo, 0x7604));
                         const float li1 = lds_f32(__byte_perm(xs[q], lo, 0x7624));

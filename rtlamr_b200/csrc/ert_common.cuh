@@ -40,6 +40,9 @@ struct DevCfg {
     DevProto proto[ERTGPU_MAX_PROTOCOLS];
 };
 
+// BlockSize is a power of two (decode.go:138, NextPowerOf2): block = s >> bs_shift, idx = s & (BS-1)
+__device__ __forceinline__ int bs_shift(const DevCfg& c) { return 31 - __clz(c.BS); }
+
 // A search hit before slicing: start position (in samples) relative to
 // (first global sample of the call) - PKL, and the preamble that matched.
 struct RawHit {

@@ -408,9 +408,11 @@ constexpr int kExtractWarps = 8;
 // If `r900_digits` is non-null it holds, per raw hit, the 42 payload digits computed by
 // r900_replay_kernel.
 __global__ void __launch_bounds__(kExtractWarps * 32, 4)
-extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, const RawHit* __restrict__ hits,
+extract_kernel(const uint32_t* __restrict__ plane, long long p0, const __grid_constant__ DevCfg cfg,
+               const RawHit* __restrict__ hits,
                unsigned long long hit_cap, const unsigned long long* __restrict__ hit_count,
-               const uint16_t* __restrict__ crc_tables, const uint16_t* __restrict__ crc_pos, Gf32 gf,
+               const uint16_t* __restrict__ crc_tables, const uint16_t* __restrict__ crc_pos,
+               const __grid_constant__ Gf32 gf,  // __grid_constant__: indexed in place, no per-thread local copy
                const uint8_t* __restrict__ r900_digits,
                long long first_block, uint32_t flags, ertgpu_candidate* __restrict__ out,
                unsigned long long out_cap, unsigned long long* __restrict__ out_count,
@@ -530,8 +532,8 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, DevCfg cfg, con
                 if (ok) mask |= 1u << i;
             }
             if (lane == 0) {
-                rec->block = first_block + (long long)(h.s / (unsigned long long)cfg.BS);
-                rec->idx = (int32_t)(h.s % (unsigned long long)cfg.BS);
+                rec->block = first_block + (long long)(h.s >> bs_shift(cfg));
+                rec->idx = (int32_t)(h.s & (unsigned long long)(cfg.BS - 1));
                 rec->preamble_id = h.preamble_id;
                 rec->check_mask = mask;
                 rec->flags = has_dig ? ERTGPU_CAND_HAS_R900 : 0u;
@@ -588,7 +590,7 @@ __global__ void r900_mark_kernel(DevCfg cfg, const RawHit* __restrict__ hits, un
     for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
         const RawHit h = hits[c];
         if (!cfg.pre_has_r900[h.preamble_id]) continue;
-        const long long b = (long long)(h.s / (unsigned long long)cfg.BS);
+        const long long b = (long long)(h.s >> bs_shift(cfg));
         if (block_slot[b] != -1) continue;
         if (atomicCAS(&block_slot[b], -1, -3) == -1) {  // -3: being assigned
             const unsigned int slot = atomicAdd(slot_count, 1u);
@@ -672,10 +674,10 @@ __global__ void r900_digits_kernel(DevCfg cfg, const RawHit* __restrict__ hits, 
         const int k = (int)(t % ERTGPU_R900_DIGITS);
         const RawHit h = hits[c];
         if (!cfg.pre_has_r900[h.preamble_id]) continue;
-        const long long b = (long long)(h.s / (unsigned long long)cfg.BS);
+        const long long b = (long long)(h.s >> bs_shift(cfg));
         const int slot = block_slot[b];
         if (slot < 0) continue;  // handled by the replay kernel
-        const int idx = (int)(h.s % (unsigned long long)cfg.BS);
+        const int idx = (int)(h.s & (unsigned long long)(cfg.BS - 1));
         const float* cs = scratch + (size_t)slot * (size_t)span + (idx + cfg.PL - cfg.SL + 4 * k * cfg.CL);
         digits[c * ERTGPU_R900_DIGITS + k] = r900_digit(cs[0], cs[cfg.CL], cs[2 * cfg.CL], cs[3 * cfg.CL], cs[4 * cfg.CL]);
     }
@@ -699,9 +701,9 @@ __global__ void r900_replay_kernel(const uint8_t* __restrict__ iq, const uint8_t
     for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
         const RawHit h = hits[c];
         if (!cfg.pre_has_r900[h.preamble_id]) continue;
-        const long long b = (long long)(h.s / (unsigned long long)cfg.BS);
+        const long long b = (long long)(h.s >> bs_shift(cfg));
         if (block_slot && block_slot[b] >= 0) continue;      // served by the per-block chain
-        const int idx = (int)(h.s % (unsigned long long)cfg.BS);
+        const int idx = (int)(h.s & (unsigned long long)(cfg.BS - 1));
         const long long first = (b + 1) * cfg.BS - cfg.BUF;  // sample of r900 signal[0]
         const int payload = idx + cfg.PL - cfg.SL;           // r900.go:187
         const int last = payload + 4 * ERTGPU_R900_DIGITS * cfg.CL;  // csum index of the final tap
