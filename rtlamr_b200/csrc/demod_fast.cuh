@@ -115,6 +115,16 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
     uint64_t r;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -305,25 +315,34 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
                         // {byte0: lane*4 (or the zero column), byte1: I or Q, bytes 2-3: LUT base >> 16}
                         const float li0 = lds_f32(__byte_perm(xs[q], lo, 0x7604));
                         const float li1 = lds_f32(__byte_perm(xs[q], lo, 0x7624));
-                        float lq0, lq1;
-                        if constexpr (HYBRID) {
-                            const float mq0 = __uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7614));  // 32768 + Q
-                            const float mq1 = __uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7634));
-                            const float nq0 = __fsub_rn(32895.5f, mq0), nq1 = __fsub_rn(32895.5f, mq1);  // 127.5 - Q, exact
-                            const float xq0 = __fmaf_rn(nq0, rh, __fmul_rn(nq0, rl));                    // fl((127.5-Q)/127.5)
-                            const float xq1 = __fmaf_rn(nq1, rh, __fmul_rn(nq1, rl));
-                            lq0 = __fmul_rn(xq0, xq0);
-                            lq1 = __fmul_rn(xq1, xq1);
-                        } else {
-                            lq0 = lds_f32(__byte_perm(xs[q], lo, 0x7614));
-                            lq1 = lds_f32(__byte_perm(xs[q], lo, 0x7634));
-                        }
                         float m0, m1, f0, f1;
-                        if constexpr (G::kPacked) {
-                            unpack2(add2(pack2(li0, li1), pack2(lq0, lq1)), m0, m1);  // decode.go:222
+                        if constexpr (HYBRID && G::kPacked) {
+                            // the four roundings of the computed Q magnitude, two samples per instruction
+                            const uint64_t mq = pack2(__uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7614)),   // 32768 + Q
+                                                      __uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7634)));
+                            const uint64_t nq = sub2(pack2(32895.5f, 32895.5f), mq);                              // 127.5 - Q, exact
+                            const uint64_t xq = fma2(nq, pack2(rh, rh), mul2(nq, pack2(rl, rl)));                 // fl((127.5-Q)/127.5)
+                            unpack2(add2(pack2(li0, li1), mul2(xq, xq)), m0, m1);                                 // decode.go:213,222
                         } else {
-                            m0 = __fadd_rn(li0, lq0);
-                            m1 = __fadd_rn(li1, lq1);
+                            float lq0, lq1;
+                            if constexpr (HYBRID) {
+                                const float mq0 = __uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7614));  // 32768 + Q
+                                const float mq1 = __uint_as_float(__byte_perm(xs[q], 0x47000000u, 0x7634));
+                                const float nq0 = __fsub_rn(32895.5f, mq0), nq1 = __fsub_rn(32895.5f, mq1);  // 127.5 - Q, exact
+                                const float xq0 = __fmaf_rn(nq0, rh, __fmul_rn(nq0, rl));                    // fl((127.5-Q)/127.5)
+                                const float xq1 = __fmaf_rn(nq1, rh, __fmul_rn(nq1, rl));
+                                lq0 = __fmul_rn(xq0, xq0);
+                                lq1 = __fmul_rn(xq1, xq1);
+                            } else {
+                                lq0 = lds_f32(__byte_perm(xs[q], lo, 0x7614));
+                                lq1 = lds_f32(__byte_perm(xs[q], lo, 0x7634));
+                            }
+                            if constexpr (G::kPacked) {
+                                unpack2(add2(pack2(li0, li1), pack2(lq0, lq1)), m0, m1);  // decode.go:222
+                            } else {
+                                m0 = __fadd_rn(li0, lq0);
+                                m1 = __fadd_rn(li1, lq1);
+                            }
                         }
                         const float c0 = __fadd_rn(c, m0);                            // csum[k+1], decode.go:234
                         c = __fadd_rn(c0, m1);

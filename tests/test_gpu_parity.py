@@ -116,6 +116,21 @@ def test_hybrid_magnitude_variant_is_bit_exact(built, monkeypatch, sample_iq):
         h.close()
 
 
+@pytest.mark.parametrize("mt,cl", [("scm", 72), ("scm,scm+,idm", 72), ("r900", 72), ("scm", 64)])
+def test_legacy_search_kernel_agrees(built, monkeypatch, mt, cl):
+    """ERTGPU_SEARCH_LEGACY=1: the per-bit-load Search kernel finds the same candidates as the sliding-window one
+    (both are compared with the oracle's list)."""
+    iq, _, _ = synth_stream(mt, cl, 1 << 21, spacing=1 << 18)
+    o, cands, msgs = oracle_run(mt, cl, iq)
+    assert len(cands) > 0
+    for legacy in ("1", "0"):
+        monkeypatch.setenv("ERTGPU_SEARCH_LEGACY", legacy)
+        h = capi.new_decoder(mt, cl)
+        got = h.decode(whole_blocks(iq, h.cfg.block_size2))
+        compare_candidates(h, got, o, cands)
+        h.close()
+
+
 def test_r900_digits_and_tap(built):
     mt, cl = "r900", 72
     iq, pk, truth = synth_stream(mt, cl, 1 << 20, spacing=1 << 18)
