@@ -303,7 +303,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
         r900_mark_kernel<<<148, 256, 0, st>>>(c, h->d_hits, h->cand_cap, h->d_counters, h->d_block_slot, h->d_slot_block,
                                               h->r900_slots, h->d_slot_count);
         CUDA_TRY(h, cudaGetLastError());
-        r900_chain_kernel<<<148 * 4, kR900ChainWarps * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c,
+        r900_chain_kernel<<<148 * 16, kR900ChainWarps * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c,
                                                                    h->d_slot_block, h->r900_slots, h->d_slot_count,
                                                                    h->r900_span, h->d_r900_scratch);
         CUDA_TRY(h, cudaGetLastError());
