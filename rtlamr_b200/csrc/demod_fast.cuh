@@ -34,6 +34,7 @@
 
 #include <cuda.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "ert_common.cuh"
@@ -426,6 +427,38 @@ inline EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
+// Per-device caches for things that are asked on every launch (a handle's calls are serialised by its owner, but
+// handles on several GPUs or threads may share these statics: a lost update only repeats an idempotent query).
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+inline int sm_count_of(int dev) {
+    static std::atomic<int> cache[64];
+    if (dev < 0 || dev >= 64) {
+        int n = 148;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        n = 148;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+// true the first time it is asked for (this flag, device): the caller then sets its per-device function attribute
+struct OncePerDevice {
+    std::atomic<unsigned long long> mask{0};
+    bool first(int dev) {
+        if (dev < 0 || dev >= 64) return true;
+        const unsigned long long bit = 1ull << dev;
+        return (mask.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+    }
+};
+
 // Shared-space address of the dynamic segment of a kernel without static shared memory (the first KiB
 // of the window is reserved by the system).  Asked from the device once: the demod kernel's map depends
 // on where the 64 KiB-aligned LUT lands, and the launch requests exactly the bytes the map needs so that
@@ -462,15 +495,24 @@ int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_sample
         smem = (int)(lut_base + kLutBytes + (uint32_t)nabove * G::kWarpBytes - sbase);
         if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
     }
-    {   // per device, so set on every launch (handles on several GPUs may live in one process)
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
+    const int dev = current_device();
+    {   // a per-device attribute (handles on several GPUs may live in one process)
+        static OncePerDevice once;
+        if (once.first(dev)) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return (int)e;
+        }
     }
     if (2 * G::kRowBytes > 2 * BS || hist_samples < 2 * G::L) return (int)cudaErrorInvalidValue;
     // the IQ bytes of the call as a 2D uint8 tensor: [nblocks rows][BlockSize2 bytes]
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return (int)cudaErrorNotSupported;
-    CUtensorMap map;
+    // the descriptor only depends on (base, rows, row length, box): calls that stream through the same
+    // staging buffer reuse it
+    struct MapKey { const void* iq; long long nblocks; int BS; };
+    static thread_local MapKey last_key = {nullptr, 0, 0};
+    static thread_local CUtensorMap map;
+    if (!(last_key.iq == iq && last_key.nblocks == nblocks && last_key.BS == BS)) {
     const cuuint64_t gdim[2] = {(cuuint64_t)(2 * BS), (cuuint64_t)nblocks};
     const cuuint64_t gstride[1] = {(cuuint64_t)(2 * BS)};
     const cuuint32_t box[2] = {(cuuint32_t)G::kRowBytes, 32u};
@@ -479,10 +521,10 @@ int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_sample
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+    last_key = {iq, nblocks, BS};
+    }
     const long long ntiles = (nblocks + 31) / 32;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count_of(dev);
     long long grid = (ntiles + W - 1) / W;
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
@@ -512,9 +554,7 @@ inline int launch_demod_fast(int variant, int warps, const uint8_t* iq, const ui
     // end in the 4th) the fuller last round of 7 wins; long calls keep 8.
     bool seven = false;
     if (warps == 0) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int sms = sm_count_of(current_device());
         const long long T = (nblocks + 31) / 32;
         const long long r8 = (T + sms * 8 - 1) / (sms * 8), r7 = (T + sms * 7 - 1) / (sms * 7);
         seven = (double)r7 * 0.93 < (double)r8;

@@ -91,7 +91,13 @@ struct ertgpu_handle {
     int64_t total_hits = 0, total_valid = 0;
     int64_t launches = 0;
     bool stage_timing = false;
-    cudaEvent_t ev_stage[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // stage timing: a pool of event sets so that nothing has to be read back between steps; the elapsed
+    // times of finished pipelines are folded into the sums when the pool is full or when somebody asks
+    static constexpr int kStageSets = 64;
+    cudaEvent_t ev_pool[kStageSets][5] = {};
+    cudaEvent_t* ev_stage = ev_pool[0];  // the set of the last enqueued pipeline
+    int stage_next = 0;                  // set the next pipeline will use
+    int stage_unread = 0;                // finished or pending sets not yet folded (the last stage_unread sets)
     bool stage_valid = false;
     double stage_sum[4] = {0, 0, 0, 0};  // accumulated since ertgpu_set_stage_timing(1)
     int64_t stage_n = 0;
@@ -169,7 +175,7 @@ void free_device(ertgpu_handle* h) {
         if (h->ev_h2d[k]) cudaEventDestroy(h->ev_h2d[k]);
         if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
     }
-    for (int k = 0; k < 5; k++) if (h->ev_stage[k]) cudaEventDestroy(h->ev_stage[k]);
+    for (auto& set : h->ev_pool) for (int k = 0; k < 5; k++) if (set[k]) cudaEventDestroy(set[k]);
     cudaFree(h->d_lut);
     cudaFree(h->d_crc);
     cudaFree(h->d_crc_pos);
@@ -186,6 +192,21 @@ void free_device(ertgpu_handle* h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     h->allocated = false;
+}
+
+// Fold the event sets of finished pipelines into the running sums (only called with no pipeline pending).
+void fold_stage_times(ertgpu_handle* h) {
+    for (int i = h->stage_unread; i > 0; i--) {
+        cudaEvent_t* set = h->ev_pool[(h->stage_next - i + 2 * ertgpu_handle::kStageSets) % ertgpu_handle::kStageSets];
+        float ms[4];
+        bool ok = true;
+        for (int k = 0; k < 4; k++) ok = ok && cudaEventElapsedTime(&ms[k], set[k], set[k + 1]) == cudaSuccess;
+        if (ok) {
+            for (int k = 0; k < 4; k++) h->stage_sum[k] += ms[k];
+            h->stage_n++;
+        }
+    }
+    h->stage_unread = 0;
 }
 
 // Enqueue the whole per-call pipeline for `nblocks` blocks whose IQ bytes are at d_iq.
@@ -207,6 +228,12 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     }
 
     const bool tm = h->stage_timing;
+    if (tm) {
+        if (h->stage_unread == ertgpu_handle::kStageSets) fold_stage_times(h);  // every earlier pipeline has been waited for
+        h->ev_stage = h->ev_pool[h->stage_next];
+        h->stage_next = (h->stage_next + 1) % ertgpu_handle::kStageSets;
+        h->stage_unread++;
+    }
     if (tm) CUDA_TRY(h, cudaEventRecord(h->ev_stage[0], st));
     // 1. magnitude + matched filter + quantize + pack
     if (h->demod_variant != 0) {
@@ -241,7 +268,9 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
             const bool half = (c.SL % 32) == 16;
 #define ERT_SLIDE_K(K)                                                                                           \
     do {                                                                                                         \
-        CUDA_TRY(h, cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                 \
+        static OncePerDevice once;                                                                               \
+        if (once.first(h->device))                                                                               \
+            CUDA_TRY(h, cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * kSlideMaxLoad + 4))); \
         K<<<grid, kSlideThreads, smem, st>>>(plane, sl, h->d_hits, h->cand_cap, h->d_counters);                  \
     } while (0)
 #define ERT_SLIDE(N, ...)                                                                    \
@@ -373,14 +402,7 @@ int collect_sync(ertgpu_handle* h) {
     }
     h->uncopied_n = std::min(no, h->cand_cap);
     h->uncopied = h->uncopied_n > 0;
-    if (h->stage_valid) {  // the pipeline's events have completed: fold them into the running sums
-        for (int k = 0; k < 4; k++) {
-            float ms = 0.0f;
-            if (cudaEventElapsedTime(&ms, h->ev_stage[k], h->ev_stage[k + 1]) == cudaSuccess) h->stage_sum[k] += ms;
-        }
-        h->stage_n++;
-    }
-    return ERTGPU_OK;
+    return ERTGPU_OK;  // stage times are folded lazily (fold_stage_times)
 }
 
 // ... and append its candidates to h->results.
@@ -612,7 +634,9 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_h2d[k], cudaEventDisableTiming));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
     }
-    for (int k = 0; k < 5; k++) CUDA_TRY(h, cudaEventCreate(&h->ev_stage[k]));
+    for (auto& set : h->ev_pool) for (int k = 0; k < 5; k++) CUDA_TRY(h, cudaEventCreate(&set[k]));
+    h->ev_stage = h->ev_pool[0];
+    (void)dynamic_smem_base();  // asked once, before the first launch needs it
     make_maglut(h->h_lut);
     make_gf32(&h->gf);
     CUDA_TRY(h, cudaMalloc(&h->d_lut, 256 * sizeof(float)));
@@ -855,10 +879,16 @@ int ertgpu_tap(ertgpu_handle* h, int32_t which, int64_t block, void* dst, size_t
 
 int ertgpu_set_stage_timing(ertgpu_handle* h, int32_t enable) {
     if (!h || !h->allocated) return ERTGPU_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->pending) {
+        int rc = collect_sync(h);
+        if (rc) return rc;
+    }
     h->stage_timing = enable != 0;
     if (enable) {
         for (int k = 0; k < 4; k++) h->stage_sum[k] = 0;
         h->stage_n = 0;
+        h->stage_unread = 0;
     }
     return ERTGPU_OK;
 }
@@ -882,6 +912,7 @@ int ertgpu_stage_ms_mean(ertgpu_handle* h, float* ms4, int64_t* n_pipelines) {
         int rc = collect_sync(h);
         if (rc) return rc;
     }
+    fold_stage_times(h);
     for (int k = 0; k < 4; k++) ms4[k] = h->stage_n ? (float)(h->stage_sum[k] / (double)h->stage_n) : 0.0f;
     if (n_pipelines) *n_pipelines = h->stage_n;
     return ERTGPU_OK;

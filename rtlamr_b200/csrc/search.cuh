@@ -623,41 +623,46 @@ r900_chain_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hi
         float* out = scratch + (size_t)slot * (size_t)span;   // out[i] = csum[i], i in [0, span)
         float s = 0.0f;
         if (lane == 0) out[0] = 0.0f;
-        // magnitudes are fetched kR900Ahead groups ahead of the sequential adds (global-load latency)
-        constexpr int kR900Ahead = 4;
-        float mq[kR900Ahead];
+        // raw IQ is fetched kR900Ahead groups ahead of the sequential adds (global-load latency).  Two things keep
+        // the loads really in flight for an in-order warp: the table lookups wait until the group is consumed,
+        // and the registers rotate by unrolling (a register move out of a pending load would wait for it).
+        constexpr int kR900Ahead = 8;
+        uint32_t rq[kR900Ahead];
 #pragma unroll
         for (int a = 0; a < kR900Ahead; a++)
-            mq[a] = (a * 32 + 1 < span) ? mag_at(iq, hist, hist_samples, hist_valid, first + a * 32 + lane, lut) : 0.0f;
-        for (int base = 0; base + 1 < span; base += 32) {
-            mbuf[warp][lane] = mq[0];
+            rq[a] = (a * 32 + 1 < span) ? raw_at(iq, hist, hist_samples, hist_valid, first + a * 32 + lane) : 0x10000u;
+        for (int base0 = 0; base0 + 1 < span; base0 += 32 * kR900Ahead) {
 #pragma unroll
-            for (int a = 0; a + 1 < kR900Ahead; a++) mq[a] = mq[a + 1];
-            mq[kR900Ahead - 1] = (base + kR900Ahead * 32 + 1 < span)
-                                     ? mag_at(iq, hist, hist_samples, hist_valid, first + base + kR900Ahead * 32 + lane, lut)
-                                     : 0.0f;
-            __syncwarp();
-            if (lane == 0) {
-                // 32 magnitudes into registers with vector loads, 32 dependent adds, vector stores back
-                float4 v[8];
-                float4* mv = reinterpret_cast<float4*>(&mbuf[warp][0]);
+            for (int a = 0; a < kR900Ahead; a++) {
+                const int base = base0 + a * 32;
+                if (base + 1 >= span) break;  // warp-uniform
+                mbuf[warp][lane] = mag_of(rq[a], lut);
+                rq[a] = (base + kR900Ahead * 32 + 1 < span)
+                            ? raw_at(iq, hist, hist_samples, hist_valid, first + base + kR900Ahead * 32 + lane)
+                            : 0x10000u;
+                __syncwarp();
+                if (lane == 0) {
+                    // 32 magnitudes into registers with vector loads, 32 dependent adds, vector stores back
+                    float4 v[8];
+                    float4* mv = reinterpret_cast<float4*>(&mbuf[warp][0]);
 #pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = mv[k];
-                float acc = s;
+                    for (int k = 0; k < 8; k++) v[k] = mv[k];
+                    float acc = s;
 #pragma unroll
-                for (int k = 0; k < 8; k++) {          // strictly left to right, r900.go:97-99
-                    acc = __fadd_rn(acc, v[k].x); v[k].x = acc;
-                    acc = __fadd_rn(acc, v[k].y); v[k].y = acc;
-                    acc = __fadd_rn(acc, v[k].z); v[k].z = acc;
-                    acc = __fadd_rn(acc, v[k].w); v[k].w = acc;
+                    for (int k = 0; k < 8; k++) {          // strictly left to right, r900.go:97-99
+                        acc = __fadd_rn(acc, v[k].x); v[k].x = acc;
+                        acc = __fadd_rn(acc, v[k].y); v[k].y = acc;
+                        acc = __fadd_rn(acc, v[k].z); v[k].z = acc;
+                        acc = __fadd_rn(acc, v[k].w); v[k].w = acc;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) mv[k] = v[k];
+                    s = acc;
                 }
-#pragma unroll
-                for (int k = 0; k < 8; k++) mv[k] = v[k];
-                s = acc;
+                __syncwarp();
+                if (base + lane + 1 < span) out[base + lane + 1] = mbuf[warp][lane];
+                __syncwarp();
             }
-            __syncwarp();
-            if (base + lane + 1 < span) out[base + lane + 1] = mbuf[warp][lane];
-            __syncwarp();
         }
     }
 }
