@@ -480,21 +480,24 @@ inline uint32_t dynamic_smem_base() {
     return base;
 }
 
+// Dynamic shared memory the kernel's map needs for W warps when the segment starts at shared address sbase:
+// [barriers 1 KiB][staging of the warps that fit][LUT at the next 64 KiB boundary][staging of the other warps]
+template <class G>
+inline int fast_smem_bytes(int W, uint32_t sbase) {
+    const uint32_t lut_base = (sbase + 1024 + 0xFFFFu) & ~0xFFFFu;
+    const int nbelow = (int)((lut_base - (sbase + 1024)) / G::kWarpBytes);
+    const int nabove = W > nbelow ? W - nbelow : 0;
+    return (int)(lut_base + kLutBytes + (uint32_t)nabove * G::kWarpBytes - sbase);
+}
+
 template <int CL, int W, int VAR = 0>
 int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_samples, int hist_valid,
                          const float* lut, uint32_t* plane_out, long long nblocks, int BS,
                          unsigned long long* tile_counter, cudaStream_t st) {
     using G = FastGeom<CL, (VAR & 2) ? 3 : 2>;
     auto kern = demod_fast_kernel<CL, W, VAR>;
-    int smem;
-    {   // mirror of the kernel's map: [barriers 1 KiB][staging][LUT at the next 64 KiB boundary][staging]
-        const uint32_t sbase = dynamic_smem_base();
-        const uint32_t lut_base = (sbase + 1024 + 0xFFFFu) & ~0xFFFFu;
-        const int nbelow = (int)((lut_base - (sbase + 1024)) / G::kWarpBytes);
-        const int nabove = W > nbelow ? W - nbelow : 0;
-        smem = (int)(lut_base + kLutBytes + (uint32_t)nabove * G::kWarpBytes - sbase);
-        if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
-    }
+    const int smem = fast_smem_bytes<G>(W, dynamic_smem_base());
+    if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
     const int dev = current_device();
     {   // a per-device attribute (handles on several GPUs may live in one process)
         static OncePerDevice once;
