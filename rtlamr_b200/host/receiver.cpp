@@ -57,6 +57,12 @@ void Receiver::Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
     }
 }
 
+void Receiver::Reset() {
+    d_.Reset();
+    prev_.clear();
+    prev_block_ = -2;
+}
+
 Stats Receiver::Run(FILE* in, bool unique, const std::function<void(const protocol::Message&)>& emit) {
     Stats st;
     const size_t bs2 = (size_t)d_.Cfg.BlockSize2;

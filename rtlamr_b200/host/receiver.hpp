@@ -39,6 +39,10 @@ public:
     // Run over a FILE* until EOF.  `emit` is called once per reported message (after dedup when unique).
     Stats Run(FILE* in, bool unique, const std::function<void(const protocol::Message&)>& emit);
 
+    // Start a new, independent stream (the next file of a batch): zeroed Decoder history (decode.go:144-145),
+    // block numbers restart at 0, empty dedup set.
+    void Reset();
+
     // The dedup step on one Decode result (messages grouped by ascending Block), exposed for tests.
     void Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
                 const std::function<void(const protocol::Message&)>& emit, Stats& st);

@@ -33,6 +33,23 @@ def test_streaming_in_small_calls_equals_one_shot(built):
     assert a[0] == "{Block:4 Idx:1031 SCM:{ID:17580293 Type: 8 Tamper:{Phy:01 Enc:01} Consumption:  111414 CRC:0xD005}}"
 
 
+def test_batch_of_files_equals_each_file_alone(built, tmp_path):
+    """Several files on one command line are independent streams through one decoder: zeroed history, block
+    numbers from 0 and an empty dedup set at every file boundary."""
+    sample = os.path.join(GOLDEN, "sample_cl78.bin")
+    other = tmp_path / "second.bin"
+    raw = np.fromfile(sample, dtype=np.uint8)
+    raw[16384 * 3:].tofile(other)                      # the same capture entered three blocks late
+    a, _ = run_cli(sample, "-msgtype=scm", "-symbollength=78")
+    b, _ = run_cli(str(other), "-msgtype=scm", "-symbollength=78")
+    out = subprocess.run([CLI, "-msgtype=scm", "-symbollength=78", "-blocks=5", sample, str(other), sample],
+                         capture_output=True, text=True, timeout=300, check=True)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines == a + b + a
+    assert len(b) >= 10 and b != a
+    assert out.stderr.count("messages (") == 3 and "second.bin: " in out.stderr
+
+
 def test_cross_block_dedup_matches_main_go_rule(built, tmp_path):
     from rtlamr_b200 import synth
     mt, cl = "scm", 72
