@@ -74,6 +74,7 @@ struct ertgpu_handle {
     int demod_warps = 0;        // 0 default; tuning override (env ERTGPU_FAST_WARPS)
     bool search_legacy = false; // env ERTGPU_SEARCH_LEGACY: the per-bit-load Search kernel (kept for chip lengths like 78 and as a cross-check)
     int sm_count = 148;
+    bool r900_chain_shfl = false;  // env ERTGPU_R900_CHAIN=shfl: the shuffle form of the r900 chain's serial sum
 
     // state of the last enqueued pipeline (for fetch and taps)
     bool pending = false;       // a pipeline is enqueued and not yet synchronised
@@ -332,9 +333,15 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
         r900_mark_kernel<<<148, 256, 0, st>>>(c, h->d_hits, h->cand_cap, h->d_counters, h->d_block_slot, h->d_slot_block,
                                               h->r900_slots, h->d_slot_count);
         CUDA_TRY(h, cudaGetLastError());
-        r900_chain_kernel<<<148 * 16, kR900ChainWarps * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c,
-                                                                   h->d_slot_block, h->r900_slots, h->d_slot_count,
-                                                                   h->r900_span, h->d_r900_scratch);
+        if (h->r900_chain_shfl) {
+            r900_chain_kernel<true><<<148 * 16, kR900ChainWarps * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c,
+                                                                       h->d_slot_block, h->r900_slots, h->d_slot_count,
+                                                                       h->r900_span, h->d_r900_scratch);
+        } else {
+            r900_chain_kernel<false><<<148 * 16, kR900ChainWarps * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c,
+                                                                       h->d_slot_block, h->r900_slots, h->d_slot_count,
+                                                                       h->r900_span, h->d_r900_scratch);
+        }
         CUDA_TRY(h, cudaGetLastError());
         r900_digits_kernel<<<148 * 4, 256, 0, st>>>(c, h->d_hits, h->cand_cap, h->d_counters, h->d_block_slot, h->r900_span,
                                                     h->d_r900_scratch, h->d_digits);
@@ -682,6 +689,7 @@ int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_cal
     h->demod_variant = demod_fast_variant(d.CL, d.BS);
     if (const char* e = getenv("ERTGPU_FAST_WARPS")) h->demod_warps = atoi(e);
     if (const char* e = getenv("ERTGPU_SEARCH_LEGACY")) h->search_legacy = atoi(e) != 0;
+    if (const char* e = getenv("ERTGPU_R900_CHAIN")) h->r900_chain_shfl = strcmp(e, "shfl") == 0;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
     if (h->sm_count < 1) h->sm_count = 148;
     h->cur_plane = h->cur_hist = 0;

@@ -606,6 +606,10 @@ __global__ void r900_mark_kernel(DevCfg cfg, const RawHit* __restrict__ hits, un
 
 constexpr int kR900ChainWarps = 4;
 
+// SHFL: the 32 magnitudes of a group stay in the lanes' registers and every lane runs the same left-to-right
+// sum over shuffled values, keeping the prefix that belongs to it -- no shared-memory round trip, no divergent
+// single-lane section, no warp barriers (same additions in the same order: identical sums).
+template <bool SHFL>
 __global__ void __launch_bounds__(kR900ChainWarps * 32)
 r900_chain_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist, int hist_samples, int hist_valid,
                   const float* __restrict__ lut_g, DevCfg cfg, const int* __restrict__ slot_block, int slot_cap,
@@ -636,10 +640,22 @@ r900_chain_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hi
             for (int a = 0; a < kR900Ahead; a++) {
                 const int base = base0 + a * 32;
                 if (base + 1 >= span) break;  // warp-uniform
-                mbuf[warp][lane] = mag_of(rq[a], lut);
+                const float mine_m = mag_of(rq[a], lut);
                 rq[a] = (base + kR900Ahead * 32 + 1 < span)
                             ? raw_at(iq, hist, hist_samples, hist_valid, first + base + kR900Ahead * 32 + lane)
                             : 0x10000u;
+                if constexpr (SHFL) {
+                    float acc = s, keep = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {          // strictly left to right, r900.go:97-99
+                        acc = __fadd_rn(acc, __shfl_sync(0xFFFFFFFFu, mine_m, k));
+                        keep = (lane == k) ? acc : keep;
+                    }
+                    s = acc;
+                    if (base + lane + 1 < span) out[base + lane + 1] = keep;
+                    continue;
+                }
+                mbuf[warp][lane] = mine_m;
                 __syncwarp();
                 if (lane == 0) {
                     // 32 magnitudes into registers with vector loads, 32 dependent adds, vector stores back

@@ -131,6 +131,27 @@ def test_legacy_search_kernel_agrees(built, monkeypatch, mt, cl):
         h.close()
 
 
+@pytest.mark.parametrize("mt,cl", [("r900", 72), ("scm,scm+,idm,r900", 72), ("r900bcd", 32)])
+def test_r900_chain_shuffle_form_agrees(built, monkeypatch, mt, cl):
+    """ERTGPU_R900_CHAIN=shfl: the r900 running sum with the serial adds done over shuffled registers (every
+    lane the same left-to-right sum) returns records identical to the shared-memory form -- digits, syndrome
+    verdicts and all -- and the candidate list of the oracle; the shared-memory form's digits are compared with
+    the oracle's quantized buffer in test_r900_digits_and_tap."""
+    iq, _, _ = synth_stream(mt, cl, 1 << 21, spacing=1 << 18)
+    o, cands, msgs = oracle_run(mt, cl, iq)
+    out = {}
+    for form in ("shfl", "smem"):
+        monkeypatch.setenv("ERTGPU_R900_CHAIN", form)
+        h = capi.new_decoder(mt, cl)
+        got = h.decode(whole_blocks(iq, h.cfg.block_size2))
+        compare_candidates(h, got, o, cands)
+        out[form] = np.sort(got, order=["block", "idx", "preamble_id"])
+        h.close()
+    assert (out["shfl"]["flags"] & capi.CAND_HAS_R900).any()
+    assert out["shfl"].tobytes() == out["smem"].tobytes()
+    assert (out["shfl"]["check_mask"] != 0).any()
+
+
 def test_r900_digits_and_tap(built):
     mt, cl = "r900", 72
     iq, pk, truth = synth_stream(mt, cl, 1 << 20, spacing=1 << 18)
