@@ -49,8 +49,46 @@ def lib():
         L.erthost_decode.restype = C.c_longlong
         L.erthost_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(_Msg), C.c_longlong]
         L.erthost_log.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.erthost_new_parse_only.restype = C.c_void_p
+        L.erthost_new_parse_only.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        L.erthost_parse.restype = C.c_longlong
+        L.erthost_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(_Msg), C.c_longlong]
         _lib = L
     return _lib
+
+
+def _messages(out, n):
+    return [HostMessage(m.block, m.idx, m.msgtype.decode(), m.meter_id, m.meter_type, bytes(m.checksum[:m.nchecksum]),
+                        m.text.decode(), tuple(m.record.decode().split(","))) for m in out[:n]]
+
+
+class Parsers:
+    """NewDecoder + RegisterProtocol(NewParser(..)) WITHOUT Allocate: no device is touched.  parse() is the second
+    half of Decode (decode.go:177-187 and every parser's Parse) on candidate records from any source."""
+
+    def __init__(self, msgtypes: str, chip_length: int = 72):
+        self._L = lib()
+        err = C.create_string_buffer(512)
+        self._h = self._L.erthost_new_parse_only(msgtypes.encode(), chip_length, err, 512)
+        if not self._h:
+            raise RuntimeError(err.value.decode())
+
+    def close(self):
+        if self._h:
+            self._L.erthost_free(self._h)
+            self._h = None
+
+    def parse(self, cands: np.ndarray, cap: int = 4096) -> list[HostMessage]:
+        """cands: structured array with capi.CAND_DTYPE, sorted by (block, preamble_id, idx)."""
+        cands = np.ascontiguousarray(cands)
+        assert cands.dtype.itemsize == 160
+        out = (_Msg * cap)()
+        n = self._L.erthost_parse(self._h, cands.ctypes.data, len(cands), out, cap)
+        if n < 0:
+            raise RuntimeError(self._L.erthost_error(self._h).decode())
+        if n > cap:
+            raise OverflowError(f"{n} messages, cap {cap}")
+        return _messages(out, n)
 
 
 class Receiver:
@@ -100,5 +138,4 @@ class Receiver:
             raise RuntimeError(self._L.erthost_error(self._h).decode())
         if n > cap:
             raise OverflowError(f"{n} messages, cap {cap}")
-        return [HostMessage(m.block, m.idx, m.msgtype.decode(), m.meter_id, m.meter_type, bytes(m.checksum[:m.nchecksum]),
-                            m.text.decode(), tuple(m.record.decode().split(","))) for m in out[:n]]
+        return _messages(out, n)

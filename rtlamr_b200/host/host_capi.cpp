@@ -45,6 +45,24 @@ erthost* erthost_new(const char* msgtypes_csv, int chip_length, int device, long
     }
 }
 
+// The same without Allocate: no device is touched, only erthost_parse works on such a handle.
+erthost* erthost_new_parse_only(const char* msgtypes_csv, int chip_length, char* errbuf, int errcap) {
+    try {
+        protocol::RegisterStockParsers();
+        auto* h = new erthost();
+        std::stringstream ss(msgtypes_csv);
+        std::string name;
+        while (std::getline(ss, name, ',')) {
+            if (name.empty()) continue;
+            h->d.RegisterProtocol(protocol::NewParser(name, chip_length));
+        }
+        return h;
+    } catch (const std::exception& e) {
+        if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", e.what());
+        return nullptr;
+    }
+}
+
 void erthost_free(erthost* h) { delete h; }
 
 const char* erthost_error(const erthost* h) { return h ? h->err.c_str() : ""; }
@@ -70,9 +88,35 @@ int erthost_reset(erthost* h) {
 
 // rcvr.d.Decode(block) for N blocks (main.go:235); returns the number of messages (all are counted,
 // the first `cap` are written), or -1 on error / -2 when len is not a multiple of BlockSize2.
+static long long fill_msgs(const std::vector<protocol::MessagePtr>& msgs, erthost_msg* out, long long cap);
+
+// The parsers alone (decode.go:177-187 + each Parse): candidates sorted by (block, preamble, idx) in, messages out.
+long long erthost_parse(erthost* h, const ertgpu_candidate* cands, long long n, erthost_msg* out, long long cap) {
+    try {
+        std::vector<protocol::MessagePtr> msgs;
+        h->d.Dispatch(cands, (size_t)n, msgs);
+        return fill_msgs(msgs, out, cap);
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return -1;
+    }
+}
+
 long long erthost_decode(erthost* h, const uint8_t* iq, size_t len, erthost_msg* out, long long cap) {
     try {
         auto msgs = h->d.Decode(iq, len);
+        return fill_msgs(msgs, out, cap);
+    } catch (const std::length_error& e) {
+        h->err = e.what();
+        return -2;
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return -1;
+    }
+}
+
+static long long fill_msgs(const std::vector<protocol::MessagePtr>& msgs, erthost_msg* out, long long cap) {
+    {
         long long n = 0;
         for (auto& m : msgs) {
             if (n < cap) {
@@ -94,12 +138,6 @@ long long erthost_decode(erthost* h, const uint8_t* iq, size_t len, erthost_msg*
             n++;
         }
         return n;
-    } catch (const std::length_error& e) {
-        h->err = e.what();
-        return -2;
-    } catch (const std::exception& e) {
-        h->err = e.what();
-        return -1;
     }
 }
 

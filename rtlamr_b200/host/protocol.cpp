@@ -568,18 +568,25 @@ std::vector<MessagePtr> Decoder::Decode(const uint8_t* input, size_t len) {
     }
     if (rc != ERTGPU_OK) raise(h_, rc, "Decode");
 
-    // Rebuild the reference's per-block, per-preamble []Data lists (decode.go:177-187) and hand each to
-    // the parsers filed under that preamble.  Candidates arrive sorted by (block, preamble, idx).
-    // Only candidates that passed a GPU screen are fetched: a parser would reject the others at its own
-    // checksum test, after the same `seen` bookkeeping, so the emitted messages are identical.
     std::vector<MessagePtr> out;
+    Dispatch(cands_.data(), n, out);
+    return out;
+}
+
+// Rebuild the reference's per-block, per-preamble []Data lists (decode.go:177-187) and hand each to
+// the parsers filed under that preamble.  Candidates arrive sorted by (block, preamble, idx).
+// Decode only fetches candidates that passed a GPU screen: a parser would reject the others at its own
+// checksum test, after the same `seen` bookkeeping, so the emitted messages are identical.
+void Decoder::Dispatch(const ertgpu_candidate* cands, size_t n, std::vector<MessagePtr>& out) {
     const size_t nbytes = (size_t)((Cfg.PacketSymbols + 7) >> 3);
     size_t i = 0;
     while (i < n) {
         size_t j = i;
         std::vector<Data> pkts;
-        while (j < n && cands_[j].block == cands_[i].block && cands_[j].preamble_id == cands_[i].preamble_id) {
-            const ertgpu_candidate& c = cands_[j];
+        if (cands[i].preamble_id < 0 || (size_t)cands[i].preamble_id >= by_pre_.size())
+            throw std::out_of_range("candidate with an unregistered preamble");
+        while (j < n && cands[j].block == cands[i].block && cands[j].preamble_id == cands[i].preamble_id) {
+            const ertgpu_candidate& c = cands[j];
             Data d = NewData(c.bytes, nbytes);
             d.Idx = c.idx;
             d.Block = c.block;
@@ -589,10 +596,9 @@ std::vector<MessagePtr> Decoder::Decode(const uint8_t* input, size_t len) {
             pkts.push_back(std::move(d));
             j++;
         }
-        for (size_t pi : by_pre_[(size_t)cands_[i].preamble_id]) parsers_[pi]->Parse(pkts, out);
+        for (size_t pi : by_pre_[(size_t)cands[i].preamble_id]) parsers_[pi]->Parse(pkts, out);
         i = j;
     }
-    return out;
 }
 
 std::string Decoder::Log() const {  // decode.go:73-90

@@ -129,6 +129,10 @@ public:
     // decode.go:163-197 for N = len/BlockSize2 consecutive blocks; throws std::length_error when len is
     // not a multiple of BlockSize2 (the reference panics with a slice-bounds error, decode.go:222)
     std::vector<MessagePtr> Decode(const uint8_t* input, size_t len);
+    // The second half of Decode (decode.go:177-187 + parse.go): candidates sorted by (block, preamble, idx) are
+    // regrouped into per-block, per-preamble []Data and handed to the parsers filed under that preamble.  Needs
+    // RegisterProtocol only (no device), so the parsers can be exercised on candidates from any source.
+    void Dispatch(const ertgpu_candidate* cands, size_t n, std::vector<MessagePtr>& out);
     std::string Log() const;  // decode.go:73-90
     void Reset();
     ertgpu_handle* Handle() const { return h_; }
