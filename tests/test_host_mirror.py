@@ -51,6 +51,39 @@ def test_parsers_alone_match_the_oracle_parsers(built, mt, cl):
     p.close()
 
 
+@pytest.mark.parametrize("mt,cl", [("r900", 72), ("r900bcd", 32)])
+def test_r900_parser_alone_with_oracle_digits(built, mt, cl):
+    """The r900 parser's byte/digit half (r900.go:195-245: digits -> 5-bit symbols -> RS syndrome -> fields) without a
+    device: candidates AND their 42 payload digits come from the oracle (its r900 `quantized` buffer, block by block)."""
+    from rtlamr_b200 import capi, host
+    iq, pk, truth = synth_stream(mt, cl, 1 << 20, spacing=1 << 18)
+    o = oracle.Oracle(mt, cl)
+    bs2 = o.cfg.block_size2
+    iq = whole_blocks(iq, bs2)
+    recs, want = [], []
+    for b in range(iq.size // bs2):
+        cands, msgs = o.decode(iq[b * bs2:(b + 1) * bs2])
+        q = o.r900_quantized()
+        want += msgs
+        rec = _cand_records(cands)
+        for r in rec:
+            payload = int(r["idx"]) + o.cfg.preamble_length - o.cfg.symbol_length
+            r["r900_digits"][:] = [int(q[payload + k * 4 * cl]) for k in range(capi.R900_DIGITS)]
+            r["flags"] = capi.CAND_HAS_R900
+        recs.append(rec)
+    p = host.Parsers(mt, cl)
+    got = p.parse(np.concatenate(recs))
+    a = sorted((m.block, m.idx, NAMES[m.msgtype], m.meter_id, m.meter_type, int(m.record[CONS_FIELD[m.msgtype]]), m.checksum)
+               for m in got)
+    b_ = sorted((m.block, m.idx, m.proto, m.meter_id, m.meter_type, m.consumption, m.checksum) for m in want)
+    assert a == b_ and len(a) >= 2
+    with pytest.raises(RuntimeError):   # an r900 candidate without digits is a programming error, not a silent miss
+        bad = np.concatenate(recs)[:1].copy()
+        bad["flags"] = 0
+        p.parse(bad)
+    p.close()
+
+
 def test_parsers_alone_on_the_golden_capture(built, sample_iq):
     """sample.bin at chip length 78, exact Search: the 853 oracle candidates give the 14 golden messages and rtlamr's
     plain formatting (scm.go:139-143)."""
