@@ -22,8 +22,10 @@
 
 namespace ert {
 
-// ---- Search -------------------------------------------------------------------------------
+// ---- Search, per-bit-load form -------------------------------------------------------------
 //
+// (The kernel for geometries the sliding-window kernel further down does not cover -- SL % 16 != 0 such as
+// chip length 78, preambles shorter than 16 bits -- and the cross-check of that kernel, ERTGPU_SEARCH_LEGACY=1.)
 // A CTA stages a tile of the bit-plane (kSearchTile words of start positions + the halo the last
 // preamble bit reaches) in shared memory; a thread then tests 32 consecutive start positions at a
 // time.  For preamble bit k every start of the word looks at the SAME relative window: word offset
