@@ -53,6 +53,9 @@ def lib():
         L.erthost_new_parse_only.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
         L.erthost_parse.restype = C.c_longlong
         L.erthost_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(_Msg), C.c_longlong]
+        L.erthost_parse_dedup.restype = C.c_longlong
+        L.erthost_parse_dedup.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.POINTER(_Msg), C.c_longlong,
+                                          C.POINTER(C.c_longlong)]
         _lib = L
     return _lib
 
@@ -89,6 +92,20 @@ class Parsers:
         if n > cap:
             raise OverflowError(f"{n} messages, cap {cap}")
         return _messages(out, n)
+
+
+def _parse_dedup(self, cands: np.ndarray, unique: bool = True, cap: int = 4096):
+    """parse() followed by the receive loop's cross-block dedup (main.go:244-260,292): (messages, duplicates dropped)."""
+    cands = np.ascontiguousarray(cands)
+    out = (_Msg * cap)()
+    dup = C.c_longlong(0)
+    n = self._L.erthost_parse_dedup(self._h, cands.ctypes.data, len(cands), 1 if unique else 0, out, cap, C.byref(dup))
+    if n < 0:
+        raise RuntimeError(self._L.erthost_error(self._h).decode())
+    return _messages(out, min(n, cap)), int(dup.value)
+
+
+Parsers.parse_dedup = _parse_dedup
 
 
 class Receiver:

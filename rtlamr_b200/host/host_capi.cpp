@@ -5,6 +5,7 @@
 #include <sstream>
 
 #include "protocol.hpp"
+#include "receiver.hpp"
 
 extern "C" {
 
@@ -96,6 +97,33 @@ long long erthost_parse(erthost* h, const ertgpu_candidate* cands, long long n, 
         std::vector<protocol::MessagePtr> msgs;
         h->d.Dispatch(cands, (size_t)n, msgs);
         return fill_msgs(msgs, out, cap);
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return -1;
+    }
+}
+
+// erthost_parse followed by the receive loop's cross-block dedup (main.go:244-260,292) with a fresh memory:
+// the messages rtlamr would print for this candidate list with -unique=`unique`.
+long long erthost_parse_dedup(erthost* h, const ertgpu_candidate* cands, long long n, int unique, erthost_msg* out,
+                              long long cap, long long* duplicates) {
+    try {
+        std::vector<protocol::MessagePtr> msgs, kept;
+        h->d.Dispatch(cands, (size_t)n, msgs);
+        receiver::BlockDedup dd;
+        receiver::Stats st;
+        std::vector<const protocol::Message*> order;
+        dd.Filter(msgs, unique != 0, [&](const protocol::Message& m) { order.push_back(&m); }, st);
+        if (duplicates) *duplicates = st.duplicates;
+        // re-own in emit order (msgs keeps the objects alive until we return)
+        std::vector<protocol::MessagePtr> view;
+        for (const protocol::Message* m : order)
+            for (auto& p : msgs)
+                if (p.get() == m) {
+                    view.push_back(std::move(p));
+                    break;
+                }
+        return fill_msgs(view, out, cap);
     } catch (const std::exception& e) {
         h->err = e.what();
         return -1;

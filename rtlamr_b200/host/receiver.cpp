@@ -34,6 +34,11 @@ Receiver::~Receiver() {
 
 void Receiver::Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
                       const std::function<void(const protocol::Message&)>& emit, Stats& st) {
+    dedup_.Filter(msgs, unique, emit, st);
+}
+
+void BlockDedup::Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
+                        const std::function<void(const protocol::Message&)>& emit, Stats& st) {
     // main.go:221-224,244-260,292: `next` collects the digests of the current block, a message whose digest
     // was seen in the previous block is skipped, and the maps swap after every block -- including blocks
     // without messages, which is why a gap in the block numbers empties `prev`.
@@ -59,8 +64,7 @@ void Receiver::Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
 
 void Receiver::Reset() {
     d_.Reset();
-    prev_.clear();
-    prev_block_ = -2;
+    dedup_.Reset();
 }
 
 Stats Receiver::Run(FILE* in, bool unique, const std::function<void(const protocol::Message&)>& emit) {

@@ -28,6 +28,23 @@ struct Stats {
     double seconds = 0;
 };
 
+// The receive loop's prev/next digest maps (main.go:221-224,244-260,292) on their own: a message whose digest was
+// reported for the previous block is dropped; a gap in the block numbers empties the memory.
+class BlockDedup {
+public:
+    // msgs grouped by ascending Block (what Decode returns); `emit` sees every message that is reported.
+    void Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
+                const std::function<void(const protocol::Message&)>& emit, Stats& st);
+    void Reset() {
+        prev_.clear();
+        prev_block_ = -2;
+    }
+
+private:
+    std::set<Digest> prev_;
+    int64_t prev_block_ = -2;
+};
+
 class Receiver {
 public:
     // msgtypes: comma list as for -msgtype ("all" = scm,scm+,idm,r900, main.go:67-73)
@@ -52,8 +69,7 @@ private:
     int64_t blocks_per_call_;
     uint8_t* buf_[2] = {nullptr, nullptr};
     size_t buf_bytes_ = 0;
-    std::set<Digest> prev_;
-    int64_t prev_block_ = -2;
+    BlockDedup dedup_;
 };
 
 }  // namespace receiver

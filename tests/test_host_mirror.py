@@ -84,6 +84,50 @@ def test_r900_parser_alone_with_oracle_digits(built, mt, cl):
     p.close()
 
 
+def test_cross_block_dedup_rule_on_the_cpu(built):
+    """main.go:244-260,292 (prev/next digest maps) in the C++ mirror, no device: parse the oracle's candidates of a
+    stream whose packets straddle block boundaries, with and without -unique, against the rule applied in Python to
+    the oracle's messages."""
+    from rtlamr_b200 import host, synth
+    mt, cl = "scm", 72
+    o = oracle.Oracle(mt, cl)
+    bs, buf, sl = o.cfg.block_size, o.cfg.buffer_length, o.cfg.symbol_length
+    n = 1 << 21
+    pk, truth = synth.make_packets(mt, cl, n, seed=7, spacing=1 << 18)
+    for i in range(1, len(pk), 2):                               # Idx of the true start = BS - 2: phases straddle
+        s0 = int(pk["start_sample"][i])
+        pk["start_sample"][i] = s0 + ((bs - 2) - (s0 + sl + buf) % bs)
+    iq = whole_blocks(synth.host_fill(0, n, 0x5EED0001, pk), o.cfg.block_size2)
+    cands, msgs = o.decode(iq)
+    by_block = {}
+    for m in msgs:
+        by_block.setdefault(m.block, []).append((m.proto, m.meter_type, m.meter_id, m.checksum))
+    kept, prev, prev_block = 0, set(), -2
+    for b in sorted(by_block):
+        if b != prev_block + 1:
+            prev = set()
+        nxt = set()
+        for d in by_block[b]:
+            nxt.add(d)
+            if d not in prev:
+                kept += 1
+        prev, prev_block = nxt, b
+    p = host.Parsers(mt, cl)
+    rec = _cand_records(cands)
+    uniq, dropped = p.parse_dedup(rec, unique=True)
+    alln, dropped_all = p.parse_dedup(rec, unique=False)
+    assert len(alln) == len(msgs) and dropped_all == 0
+    assert len(uniq) == kept and dropped == len(msgs) - kept
+    assert kept < len(msgs), "the stream should contain at least one packet that spans two blocks"
+    assert {m.meter_id for m in uniq} == {m.meter_id for m in msgs}
+    # a gap in the block numbers empties the memory: the same candidates two blocks later are all reported again
+    later = rec.copy()
+    later["block"] += int(rec["block"].max()) + 3
+    twice, dropped2 = p.parse_dedup(np.concatenate([rec, later]), unique=True)
+    assert len(twice) == 2 * kept and dropped2 == 2 * dropped
+    p.close()
+
+
 def test_parsers_alone_on_the_golden_capture(built, sample_iq):
     """sample.bin at chip length 78, exact Search: the 853 oracle candidates give the 14 golden messages and rtlamr's
     plain formatting (scm.go:139-143)."""
