@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ERTGPU_ABI_VERSION 1
+#define ERTGPU_ABI_VERSION 2
 
 /* error codes */
 #define ERTGPU_OK 0
@@ -198,9 +198,45 @@ int ertgpu_tap(ertgpu_handle *h, int32_t which, int64_t block, void *dst, size_t
  * -1 restores the automatic choice of a chip-length-specialised kernel. */
 int ertgpu_set_demod_variant(ertgpu_handle *h, int32_t variant);
 
-/* Pinned host memory for callers that can use it (cudaHostAlloc/cudaFreeHost). */
+/* Pinned host memory for callers that can use it (cudaHostAlloc/cudaFreeHost).  ertgpu_decode
+ * accepts any host memory: pinned input is copied to the device directly; ordinary (pageable)
+ * input -- a Go slice, the block buffer of main.go:166 -- is staged through pinned buffers the
+ * handle owns (the copy into them runs on a few host threads and overlaps the H2D transfer of
+ * the previous chunk), so the caller never has to know. */
 int ertgpu_host_alloc(void **out, size_t nbytes);
 int ertgpu_host_free(void *p);
+
+/* Restrict the CALLING thread to the CPUs next to `device` (the PCI device's local_cpulist in
+ * sysfs), so that the pinned buffers it allocates afterwards and the staging copies it runs are
+ * NUMA-local to the GPU.  Optional; *ncpus = CPUs in the new mask, *numa_node = the device's
+ * node (-1 unknown).  Returns ERTGPU_EINVAL when the topology cannot be read (nothing changed). */
+int ertgpu_bind_host_thread(int32_t device, int32_t *ncpus, int32_t *numa_node);
+
+/* Names of the kernel instantiations the last decode launched (for bench.py's roofline label). */
+const char *ertgpu_last_kernels(const ertgpu_handle *h);
+
+/* ---- one stream over several GPUs (main.go:207-235 is where the
+ * reference would hang such a driver) ------------------------------------------------- */
+
+/* Shard r of a stream of total_blocks reference blocks cut into nshards contiguous block-aligned
+ * shards: the shard REPORTS the candidates of blocks [first_block, last_block) and must be FED
+ * from first_fed_block (halo: ceil(PacketLength/BlockSize) blocks of Quantized history,
+ * decode.go:166, plus one block of Signal lead-in, decode.go:165). */
+typedef struct {
+    int64_t first_block, last_block, first_fed_block;
+} ertgpu_shard;
+int ertgpu_plan_shards(int64_t total_blocks, int32_t nshards, int32_t block_size, int32_t packet_length,
+                       ertgpu_shard *out /* [nshards] */);
+
+/* N consecutive Decoder.Decode calls on a FRESH stream, spread over nhandles handles (normally
+ * one per GPU; several on one GPU also work): handle r decodes shard r (halo + owned blocks) of
+ * the host buffer on its own device from its own host thread, candidates of halo blocks are
+ * dropped, block numbers are made global and the lists are concatenated in (block, preamble,
+ * idx) order -- the same list one handle returns for the whole buffer after ertgpu_reset.
+ * All handles must be allocated with the same protocols; each is reset first.  There is no
+ * collective: shards are independent (every candidate is decided inside one shard + halo). */
+int ertgpu_decode_sharded(ertgpu_handle *const *handles, int32_t nhandles, const uint8_t *iq, size_t nbytes,
+                          uint32_t flags, ertgpu_candidate *out, size_t cap, size_t *n_out);
 
 /* ---- synthetic input (bench/test tooling, not part of the reference API) -- */
 

@@ -26,10 +26,9 @@ MAX_PKT = 96
 
 def build(force: bool = False) -> str:
     """Compile libert_oracle.so with the committed Makefile (gcc only)."""
-    src = os.path.join(_HERE, "ert_oracle.c")
-    hdr = os.path.join(_HERE, "ert_oracle.h")
+    srcs = [os.path.join(_HERE, f) for f in ("ert_oracle.c", "ert_oracle_bench.c", "ert_oracle.h", "Makefile")]
     if (force or not os.path.exists(_LIB_PATH)
-            or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)):
         subprocess.run(["make", "-C", _HERE, "-B", "libert_oracle.so"], check=True,
                        stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -105,6 +104,11 @@ def lib():
         L.ert_crc_checksum.restype = C.c_uint16
         L.ert_crc_checksum.argtypes = [C.c_uint16, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint16)]
         L.ert_gf32_syndrome.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p]
+        L.ert_oracle_bench_threads.restype = C.c_double
+        L.ert_oracle_bench_threads.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                               C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                               C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.ert_oracle_host_cpus.restype = C.c_int32
         _lib = L
     return _lib
 
@@ -136,6 +140,35 @@ def gf32_syndrome(message: bytes, nparity: int = 5, offset: int = 29) -> bytes:
 def maglut() -> np.ndarray:
     p = lib().ert_oracle_maglut()
     return np.ctypeslib.as_array(p, shape=(256,)).copy()
+
+
+def host_cpus() -> int:
+    """CPUs this process may run on."""
+    return int(lib().ert_oracle_host_cpus())
+
+
+def bench_threads(msgtypes, chip_length: int, iq, nthreads: int, repeats: int = 1, search: int = SEARCH_GO,
+                  pin: bool = True):
+    """Timed CPU baseline (ert_oracle_bench.c): `nthreads` independent decoders over contiguous
+    block-aligned shards of `iq` (numpy uint8 or (address, nbytes)), everything inside C (no GIL,
+    no allocation in the timed region).  Returns (seconds, n_candidates, n_messages, nblocks)."""
+    ids = proto_ids(msgtypes)
+    arr = (C.c_int32 * len(ids))(*ids)
+    probe = Oracle(msgtypes, chip_length, search)
+    bs2 = probe.cfg.block_size2
+    probe.close()
+    if isinstance(iq, tuple):
+        addr, nbytes = iq
+    else:
+        iq = np.ascontiguousarray(iq, dtype=np.uint8)
+        addr, nbytes = iq.ctypes.data, iq.size
+    nblocks = nbytes // bs2
+    nc, nm = C.c_int64(0), C.c_int64(0)
+    dt = lib().ert_oracle_bench_threads(arr, len(ids), chip_length, search, addr, nblocks, nthreads, repeats,
+                                        1 if pin else 0, C.byref(nc), C.byref(nm))
+    if dt < 0:
+        raise RuntimeError("ert_oracle_bench_threads failed")
+    return dt, nc.value, nm.value, nblocks
 
 
 class Oracle:

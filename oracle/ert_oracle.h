@@ -129,6 +129,16 @@ uint16_t ert_crc_checksum(uint16_t init, const uint8_t *data, size_t n,
 void ert_gf32_syndrome(const uint8_t *message, int32_t n, int32_t nparity, int32_t offset,
                        uint8_t *syndrome);
 
+/* ert_oracle_bench.c: the timed CPU baseline.  `nthreads` independent decoders (one per thread,
+ * like the reference's single DSP goroutine, main.go:207-235) over contiguous block-aligned
+ * shards of one stream of `nblocks` blocks, each decoded `repeats` times in BlockSize2-byte
+ * Decode calls.  Returns wall seconds (common start to last finish), < 0 on failure. */
+double ert_oracle_bench_threads(const int32_t *protos, int32_t nprotos, int32_t chip_length,
+                                int32_t search_mode, const uint8_t *iq, int64_t nblocks,
+                                int32_t nthreads, int32_t repeats, int32_t pin,
+                                int64_t *ncands, int64_t *nmsgs);
+int32_t ert_oracle_host_cpus(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,10 @@ class Candidate(C.Structure):
                 ("pad", C.c_uint8 * 2)]
 
 
+class Shard(C.Structure):
+    _fields_ = [("first_block", C.c_int64), ("last_block", C.c_int64), ("first_fed_block", C.c_int64)]
+
+
 class SynthPacket(C.Structure):
     _fields_ = [("start_sample", C.c_int64), ("n_chips", C.c_int32), ("chip_length", C.c_int32),
                 ("amp_i", C.c_int16), ("amp_q", C.c_int16), ("chips", C.c_uint8 * 192),
@@ -66,6 +70,7 @@ EXPORTS = [
     "ertgpu_last_counts", "ertgpu_last_launches", "ertgpu_set_stage_timing",
     "ertgpu_last_stage_ms", "ertgpu_stage_ms_mean", "ertgpu_tap", "ertgpu_set_demod_variant",
     "ertgpu_host_alloc", "ertgpu_host_free", "ertgpu_synth_fill",
+    "ertgpu_bind_host_thread", "ertgpu_last_kernels", "ertgpu_plan_shards", "ertgpu_decode_sharded",
 ]
 
 _lib = None
@@ -113,6 +118,11 @@ def lib() -> C.CDLL:
     L.ertgpu_host_alloc.argtypes = [C.POINTER(vp), sz]
     L.ertgpu_host_free.argtypes = [vp]
     L.ertgpu_synth_fill.argtypes = [i32, vp, i64, i64, u64, vp, i64, vp]
+    L.ertgpu_bind_host_thread.argtypes = [i32, C.POINTER(i32), C.POINTER(i32)]
+    L.ertgpu_last_kernels.restype = C.c_char_p
+    L.ertgpu_last_kernels.argtypes = [vp]
+    L.ertgpu_plan_shards.argtypes = [i64, i32, i32, i32, C.POINTER(Shard)]
+    L.ertgpu_decode_sharded.argtypes = [C.POINTER(vp), i32, vp, sz, u32, vp, sz, C.POINTER(sz)]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError if the library does not export it
     _lib = L
@@ -225,6 +235,13 @@ class Handle:
         self._check(self._L.ertgpu_stage_ms_mean(self._h, ms, C.byref(n)))
         return dict(zip(("demod", "search", "extract", "carry"), [float(x) for x in ms])), n.value
 
+    def demod_kernel_name(self) -> str:
+        """The demod instantiation the last decode launched (first entry of ertgpu_last_kernels)."""
+        return (self._L.ertgpu_last_kernels(self._h) or b"").decode().split(";")[0].strip()
+
+    def last_kernels(self) -> str:
+        return (self._L.ertgpu_last_kernels(self._h) or b"").decode()
+
     def tap(self, which: int, block: int) -> np.ndarray:
         n = C.c_size_t(0)
         self._check(self._L.ertgpu_tap(self._h, which, block, None, 0, C.byref(n)))
@@ -246,6 +263,43 @@ def new_decoder(msgtypes, chip_length: int = 72, device: int = 0, max_blocks_per
         h.register(stock_protocol(m, chip_length))
     h.allocate(device, max_blocks_per_call, max_candidates)
     return h
+
+
+def bind_host_thread(device: int):
+    """ertgpu_bind_host_thread: pin the calling thread to the CPUs next to `device`.  Returns a
+    small dict for the bench line (None fields when the topology is unknown: nothing changed)."""
+    n, node = C.c_int32(0), C.c_int32(-1)
+    rc = lib().ertgpu_bind_host_thread(device, C.byref(n), C.byref(node))
+    return {"bound": rc == OK, "cpus": n.value if rc == OK else None, "numa_node": node.value if node.value >= 0 else None}
+
+
+def plan_shards(total_blocks: int, nshards: int, block_size: int, packet_length: int):
+    arr = (Shard * nshards)()
+    rc = lib().ertgpu_plan_shards(total_blocks, nshards, block_size, packet_length, arr)
+    if rc != OK:
+        raise ErtGpuError(rc, "ertgpu_plan_shards: bad request")
+    return [(s.first_block, s.last_block, s.first_fed_block) for s in arr]
+
+
+def decode_sharded(handles, iq, flags: int = 0, cap: int = 1 << 16) -> np.ndarray:
+    """ertgpu_decode_sharded: one host buffer over several handles (one host thread per handle)."""
+    if isinstance(iq, tuple):
+        addr, nbytes = iq
+    else:
+        iq = np.ascontiguousarray(iq, dtype=np.uint8)
+        addr, nbytes = iq.ctypes.data, iq.size
+    hs = (C.c_void_p * len(handles))(*[h._h for h in handles])
+    while True:
+        out = np.empty(cap, dtype=CAND_DTYPE)
+        n = C.c_size_t(0)
+        rc = lib().ertgpu_decode_sharded(hs, len(handles), addr, nbytes, flags, out.ctypes.data, cap, C.byref(n))
+        if rc == ECAPACITY and n.value > cap:
+            cap = n.value
+            continue
+        if rc != OK:
+            msgs = [(lib().ertgpu_last_error(h._h) or b"").decode() for h in handles]
+            raise ErtGpuError(rc, "; ".join(m for m in msgs if m) or "ertgpu_decode_sharded failed")
+        return out[:n.value].copy()
 
 
 def synth_fill(device: int, d_ptr: int, first_sample: int, nsamples: int, seed: int,

@@ -493,7 +493,9 @@ inline int fast_smem_bytes(int W, uint32_t sbase) {
 template <int CL, int W, int VAR = 0>
 int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_samples, int hist_valid,
                          const float* lut, uint32_t* plane_out, long long nblocks, int BS,
-                         unsigned long long* tile_counter, cudaStream_t st) {
+                         unsigned long long* tile_counter, cudaStream_t st, int* w_out, int* var_out) {
+    if (w_out) *w_out = W;
+    if (var_out) *var_out = VAR;
     using G = FastGeom<CL, (VAR & 2) ? 3 : 2>;
     auto kern = demod_fast_kernel<CL, W, VAR>;
     const int smem = fast_smem_bytes<G>(W, dynamic_smem_base());
@@ -549,8 +551,9 @@ inline int demod_fast_variant(int CL, int BS) {
 // warps == 0 picks the default resident-warp count for the chip length
 inline int launch_demod_fast(int variant, int warps, const uint8_t* iq, const uint8_t* hist, int hist_samples,
                              int hist_valid, const float* lut, uint32_t* plane_out, long long nblocks,
-                             int BS, unsigned long long* tile_counter, cudaStream_t st) {
-#define ERT_FAST_ARGS iq, hist, hist_samples, hist_valid, lut, plane_out, nblocks, BS, tile_counter, st
+                             int BS, unsigned long long* tile_counter, cudaStream_t st, int* w_out = nullptr,
+                             int* var_out = nullptr) {
+#define ERT_FAST_ARGS iq, hist, hist_samples, hist_valid, lut, plane_out, nblocks, BS, tile_counter, st, w_out, var_out
     // Work tiles are handed out in rounds of (SMs x resident warps).  With two warps per scheduler the SM's
     // rate still grows almost linearly with the warp count (measured round time, 7 : 8 warps = 0.93 : 1), so
     // when 7 warps need no more rounds than 8 (e.g. 4096 tiles of a 1 GiB scm call: 3.95 vs 3.46 rounds, both

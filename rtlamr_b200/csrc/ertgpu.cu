@@ -11,13 +11,18 @@
 //             replaces Decoder.Quantized (1 byte per bit) and Decoder.packed
 //   hits    : (start, preamble) pairs found by search_kernel
 //   out     : ertgpu_candidate records produced by extract_kernel
+#include <ctype.h>
+#include <sched.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "demod_fast.cuh"
@@ -53,6 +58,9 @@ struct ertgpu_handle {
     int hist_valid = 0;
     uint8_t* d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
+    uint8_t* h_stage[2] = {nullptr, nullptr};  // pinned staging of pageable input (allocated on first use)
+    size_t h_stage_bytes = 0;
+    std::string kernels;                        // instantiations launched by the last pipeline
     RawHit* d_hits = nullptr;
     uint8_t* d_digits = nullptr;
     int* d_block_slot = nullptr;      // r900: scratch slot of each block of the call (-1 none)
@@ -169,29 +177,38 @@ void make_gf32(Gf32* g) {
 void free_device(ertgpu_handle* h) {
     if (!h->allocated) return;
     cudaSetDevice(h->device);
+    auto dfree = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+    auto evfree = [](cudaEvent_t& e) { if (e) cudaEventDestroy(e); e = nullptr; };
     for (int k = 0; k < 2; k++) {
-        cudaFree(h->d_plane[k]);
-        cudaFree(h->d_hist[k]);
-        cudaFree(h->d_stage[k]);
-        if (h->ev_h2d[k]) cudaEventDestroy(h->ev_h2d[k]);
-        if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
+        dfree(h->d_plane[k]);
+        dfree(h->d_hist[k]);
+        dfree(h->d_stage[k]);
+        if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]);
+        h->h_stage[k] = nullptr;
+        evfree(h->ev_h2d[k]);
+        evfree(h->ev_done[k]);
     }
-    for (auto& set : h->ev_pool) for (int k = 0; k < 5; k++) if (set[k]) cudaEventDestroy(set[k]);
-    cudaFree(h->d_lut);
-    cudaFree(h->d_crc);
-    cudaFree(h->d_crc_pos);
-    cudaFree(h->d_hits);
-    cudaFree(h->d_digits);
-    cudaFree(h->d_block_slot);
-    cudaFree(h->d_slot_block);
-    cudaFree(h->d_slot_count);
-    cudaFree(h->d_r900_scratch);
-    cudaFree(h->d_out);
-    cudaFree(h->d_counters);
-    cudaFree(h->d_tap);
+    h->stage_bytes = h->h_stage_bytes = 0;
+    for (auto& set : h->ev_pool) for (int k = 0; k < 5; k++) evfree(set[k]);
+    dfree(h->d_lut);
+    dfree(h->d_crc);
+    dfree(h->d_crc_pos);
+    dfree(h->d_hits);
+    dfree(h->d_digits);
+    dfree(h->d_block_slot);
+    dfree(h->d_slot_block);
+    dfree(h->d_slot_count);
+    dfree(h->d_r900_scratch);
+    dfree(h->d_out);
+    dfree(h->d_counters);
+    dfree(h->d_tap);
     if (h->h_counters) cudaFreeHost(h->h_counters);
+    h->h_counters = nullptr;
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    h->stream = h->copy_stream = nullptr;
+    h->pending = h->uncopied = false;
+    h->last_plane = nullptr;
     h->allocated = false;
 }
 
@@ -237,11 +254,16 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     }
     if (tm) CUDA_TRY(h, cudaEventRecord(h->ev_stage[0], st));
     // 1. magnitude + matched filter + quantize + pack
+    char kname[160];
     if (h->demod_variant != 0) {
+        int w_used = 0, var_used = 0;
         int rc = launch_demod_fast(h->demod_variant, h->demod_warps, d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut,
-                                   plane + c.hist_words, nblocks, c.BS, h->d_counters + 3, st);
+                                   plane + c.hist_words, nblocks, c.BS, h->d_counters + 3, st, &w_used, &var_used);
         if (rc != 0) return fail(h, ERTGPU_ECUDA, "demod_fast launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        snprintf(kname, sizeof(kname), "demod_fast_kernel<%d,%d,%d>", h->demod_variant, w_used, var_used);
+        h->kernels = kname;
     } else {
+        h->kernels = "demod_generic_kernel";
         int nthr = 128;
         while (nthr > 32 && (256 + 2 * (size_t)c.CL * nthr) * sizeof(float) > 200 * 1024) nthr >>= 1;
         const size_t smem = (256 + 2 * (size_t)c.CL * nthr) * sizeof(float);
@@ -441,6 +463,25 @@ int deliver(ertgpu_handle* h, ertgpu_candidate* out, size_t cap, size_t* n_out) 
     return ERTGPU_OK;
 }
 
+// memcpy on up to `nthreads` host threads (one memcpy stream does not fill the memory bus of a server CPU)
+void parallel_copy(uint8_t* dst, const uint8_t* src, size_t n, int nthreads) {
+    const size_t kMin = 4u << 20;
+    int t = (int)std::min<size_t>((size_t)nthreads, (n + kMin - 1) / kMin);
+    if (t <= 1) {
+        memcpy(dst, src, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    th.reserve((size_t)t - 1);
+    const size_t per = ((n / (size_t)t) + 4095) & ~(size_t)4095;
+    for (int i = 1; i < t; i++) {
+        const size_t a = std::min(n, per * (size_t)i), b = std::min(n, per * (size_t)(i + 1));
+        if (b > a) th.emplace_back([=] { memcpy(dst + a, src + a, b - a); });
+    }
+    memcpy(dst, src, std::min(n, per));
+    for (auto& x : th) x.join();
+}
+
 void begin_call(ertgpu_handle* h) {
     h->results.clear();
     h->uncopied = false;
@@ -538,9 +579,24 @@ int ertgpu_register_protocol(ertgpu_handle* h, const ertgpu_protocol* p) {
     return ERTGPU_OK;
 }
 
+static int allocate_impl(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_call, int64_t max_candidates);
+
 int ertgpu_allocate(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_call, int64_t max_candidates) {
     if (!h) return ERTGPU_EINVAL;
     if (h->allocated) return fail(h, ERTGPU_EINVAL, "already allocated");
+    const int rc = allocate_impl(h, device, max_blocks_per_call, max_candidates);
+    if (rc != ERTGPU_OK) {
+        // a half-built handle must not pass the `allocated` checks of decode/tap/reset: release whatever was
+        // created (the message of the failure is kept) and leave the handle ready for another ertgpu_allocate
+        const std::string msg = h->err;
+        free_device(h);
+        h->cfg.n_preambles = 0;
+        h->err = msg;
+    }
+    return rc;
+}
+
+static int allocate_impl(ertgpu_handle* h, int32_t device, int64_t max_blocks_per_call, int64_t max_candidates) {
     if (h->protos.empty()) return fail(h, ERTGPU_EINVAL, "no protocol registered");
 
     // decode.go:131-141
@@ -780,15 +836,43 @@ int ertgpu_decode(ertgpu_handle* h, const uint8_t* iq, size_t nbytes, uint32_t f
             cudaFree(h->d_stage[k]);
             h->d_stage[k] = nullptr;
         }
+        h->stage_bytes = 0;
+        for (int k = 0; k < 2; k++) CUDA_TRY(h, cudaMalloc(&h->d_stage[k], (size_t)chunk_blocks * bs2));
         h->stage_bytes = (size_t)chunk_blocks * bs2;
-        for (int k = 0; k < 2; k++) CUDA_TRY(h, cudaMalloc(&h->d_stage[k], h->stage_bytes));
     }
+    // Pinned (or registered / managed) input goes to the device directly.  Ordinary pageable memory -- a Go slice,
+    // main.go:166's block buffer -- would make every cudaMemcpyAsync a synchronous driver-staged copy: it is staged
+    // through two pinned buffers of the handle instead, filled by a few host threads while the previous chunk's
+    // transfer is in flight.
+    bool pageable = true;
+    {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, iq) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
+        else cudaGetLastError();
+    }
+    if (pageable && h->h_stage_bytes < h->stage_bytes) {
+        for (int k = 0; k < 2; k++) {
+            if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]);
+            h->h_stage[k] = nullptr;
+        }
+        h->h_stage_bytes = 0;
+        for (int k = 0; k < 2; k++) CUDA_TRY(h, cudaHostAlloc(&h->h_stage[k], h->stage_bytes, cudaHostAllocDefault));
+        h->h_stage_bytes = h->stage_bytes;
+    }
+    int copy_threads = 4;
+    if (const char* e = getenv("ERTGPU_STAGE_THREADS")) copy_threads = std::min(64, std::max(1, atoi(e)));
     int64_t done = 0, launches = 0;
     for (int64_t i = 0; done < nblocks; i++) {
         const int k = (int)(i & 1);
         const int64_t nb = std::min(chunk_blocks, nblocks - done);
-        if (i >= 2) CUDA_TRY(h, cudaEventSynchronize(h->ev_done[k]));
-        CUDA_TRY(h, cudaMemcpyAsync(h->d_stage[k], iq + (size_t)done * bs2, (size_t)nb * bs2, cudaMemcpyHostToDevice, h->copy_stream));
+        if (i >= 2) CUDA_TRY(h, cudaEventSynchronize(h->ev_done[k]));  // the kernels that read d_stage[k] (and its H2D) are done
+        const uint8_t* src = iq + (size_t)done * bs2;
+        const size_t nbytes_chunk = (size_t)nb * bs2;
+        if (pageable) {
+            parallel_copy(h->h_stage[k], src, nbytes_chunk, copy_threads);
+            src = h->h_stage[k];
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_stage[k], src, nbytes_chunk, cudaMemcpyHostToDevice, h->copy_stream));
         CUDA_TRY(h, cudaEventRecord(h->ev_h2d[k], h->copy_stream));
         if (i >= 1) {
             int rc = collect(h);
@@ -925,6 +1009,64 @@ int ertgpu_stage_ms_mean(ertgpu_handle* h, float* ms4, int64_t* n_pipelines) {
     if (n_pipelines) *n_pipelines = h->stage_n;
     return ERTGPU_OK;
 }
+
+// "0-31,64-95" -> cpu_set_t; returns the number of CPUs
+static int parse_cpulist(const char* str, cpu_set_t* set) {
+    CPU_ZERO(set);
+    int n = 0;
+    const char* p = str;
+    while (*p) {
+        char* end = nullptr;
+        long a = strtol(p, &end, 10);
+        if (end == p) break;
+        long b = a;
+        p = end;
+        if (*p == '-') {
+            b = strtol(p + 1, &end, 10);
+            if (end == p + 1) break;
+            p = end;
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++)
+            if (c >= 0 && !CPU_ISSET((int)c, set)) { CPU_SET((int)c, set); n++; }
+        while (*p == ',' || *p == ' ' || *p == '\n') p++;
+    }
+    return n;
+}
+
+int ertgpu_bind_host_thread(int32_t device, int32_t* ncpus, int32_t* numa_node) {
+    if (ncpus) *ncpus = 0;
+    if (numa_node) *numa_node = -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+        cudaGetLastError();
+        return ERTGPU_ECUDA;
+    }
+    for (char* c = bus; *c; c++) *c = (char)tolower((unsigned char)*c);
+    char path[128], buf[4096] = {0};
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    if (FILE* f = fopen(path, "r")) {
+        int node = -1;
+        if (fscanf(f, "%d", &node) == 1 && numa_node) *numa_node = node;
+        fclose(f);
+    }
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return ERTGPU_EINVAL;
+    const size_t got = fread(buf, 1, sizeof(buf) - 1, f);
+    fclose(f);
+    buf[got] = 0;
+    cpu_set_t want, allowed, both;
+    if (parse_cpulist(buf, &want) <= 0) return ERTGPU_EINVAL;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return ERTGPU_EINVAL;
+    CPU_AND(&both, &want, &allowed);
+    const int n = CPU_COUNT(&both);
+    if (n <= 0) return ERTGPU_EINVAL;          // the GPU's CPUs are outside this process's cpuset: leave it alone
+    if (sched_setaffinity(0, sizeof(both), &both) != 0) return ERTGPU_EINVAL;
+    if (ncpus) *ncpus = n;
+    return ERTGPU_OK;
+}
+
+const char* ertgpu_last_kernels(const ertgpu_handle* h) { return h ? h->kernels.c_str() : ""; }
 
 int ertgpu_host_alloc(void** out, size_t nbytes) {
     if (!out) return ERTGPU_EINVAL;

@@ -252,21 +252,30 @@ def _host_lib():
     if _host is None:
         src = os.path.join(_HERE, "csrc", "synth_host.c")
         if not os.path.exists(_HOST_LIB) or os.path.getmtime(_HOST_LIB) < os.path.getmtime(src):
-            subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-o", _HOST_LIB, src], check=True)
+            subprocess.run(["gcc", "-O2", "-fPIC", "-pthread", "-shared", "-o", _HOST_LIB, src], check=True)
         L = C.CDLL(_HOST_LIB)
         L.ertsynth_host_fill.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_int64]
         L.ertsynth_host_fill.restype = None
+        L.ertsynth_host_fill_mt.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_int64, C.c_int32]
+        L.ertsynth_host_fill_mt.restype = None
         _host = L
     return _host
 
 
-def host_fill(first_sample: int, nsamples: int, seed: int, packets: np.ndarray | None) -> np.ndarray:
-    """The synthetic stream on the CPU (bit-identical to ertgpu_synth_fill)."""
-    out = np.empty(2 * nsamples, dtype=np.uint8)
+def host_fill(first_sample: int, nsamples: int, seed: int, packets: np.ndarray | None,
+              nthreads: int = 1, out: np.ndarray | None = None) -> np.ndarray:
+    """The synthetic stream on the CPU (bit-identical to ertgpu_synth_fill); `nthreads` > 1 fills
+    disjoint ranges in parallel (same bytes: the generator is counter based)."""
+    if out is None:
+        out = np.empty(2 * nsamples, dtype=np.uint8)
+    assert out.dtype == np.uint8 and out.size >= 2 * nsamples and out.flags.c_contiguous
     if packets is None or len(packets) == 0:
         ptr, n = None, 0
     else:
         packets = np.ascontiguousarray(packets)
         ptr, n = packets.ctypes.data, len(packets)
-    _host_lib().ertsynth_host_fill(out.ctypes.data, first_sample, nsamples, seed, ptr, n)
-    return out
+    if nthreads > 1:
+        _host_lib().ertsynth_host_fill_mt(out.ctypes.data, first_sample, nsamples, seed, ptr, n, nthreads)
+    else:
+        _host_lib().ertsynth_host_fill(out.ctypes.data, first_sample, nsamples, seed, ptr, n)
+    return out[:2 * nsamples]

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in ertgpu.h but not exported"
     assert set(capi.EXPORTS) == declared
-    assert L.ertgpu_abi_version() == 1
+    assert L.ertgpu_abi_version() == 2
 
 
 def test_struct_layouts_match_header(built):

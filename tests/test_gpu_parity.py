@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import cand_key_gpu, cand_key_oracle, oracle_run, synth_stream, whole_blocks
+from helpers import assert_check_masks_exact, cand_key_gpu, cand_key_oracle, oracle_run, synth_stream, whole_blocks
 from rtlamr_b200 import capi
 
 pytestmark = pytest.mark.gpu
@@ -86,12 +86,23 @@ def test_synthetic_candidates_match_oracle(built, mt, cl, variant):
         assert any(v & (1 << bit_of[m.proto]) for v in masks), m
         accepted_bytes.setdefault(m.proto, set()).add(m.data)
     assert len(msgs) >= 1
-    # quantized plane bit-exact at three blocks
+    # ... and the converse, for EVERY candidate: a bit is set iff that parser's check passes on the returned bytes
+    assert_check_masks_exact(got, mt)
+    # every tap of the last block, for every geometry and both kernels (Signal/csum: identical, bar is 1 ulp)
     nblk = iq.size // h.cfg.block_size2
+    assert np.array_equal(h.tap(capi.TAP_QUANTIZED, nblk - 1), o.quantized())
+    assert np.array_equal(h.tap(capi.TAP_PACKED, nblk - 1), o.packed())
+    assert ulp_diff(h.tap(capi.TAP_SIGNAL, nblk - 1), o.signal()) <= 1
+    assert ulp_diff(h.tap(capi.TAP_CSUM, nblk - 1), o.csum()) <= 1
+    assert np.array_equal(h.tap(capi.TAP_SIGNAL, nblk - 1), o.signal())
+    assert np.array_equal(h.tap(capi.TAP_CSUM, nblk - 1), o.csum())
+    # ... and of a block in the middle (DSP only: Search/Parse do not change the taps)
     o2 = oracle.Oracle(mt, cl, oracle.SEARCH_EXACT)
-    for b in range(nblk):
+    mid = nblk // 2
+    for b in range(mid + 1):
         o2.dsp_only(iq[b * h.cfg.block_size2:(b + 1) * h.cfg.block_size2])
-    assert np.array_equal(h.tap(capi.TAP_QUANTIZED, nblk - 1), o2.quantized())
+    assert np.array_equal(h.tap(capi.TAP_QUANTIZED, mid), o2.quantized())
+    assert np.array_equal(h.tap(capi.TAP_CSUM, mid), o2.csum())
     h.close()
 
 
