@@ -139,9 +139,12 @@ constexpr int fast_body_len(int CL) {
     return L;
 }
 
-template <int CL, int STAGES = 2>
+// the tight ring: L = CL (every slot is read, then overwritten, in the same step) when CL / 8 is odd
+constexpr bool fast_tight_ok(int CL) { return CL % 8 == 0 && ((CL / 8) & 1) == 1; }
+
+template <int CL, int STAGES = 2, bool TIGHT = false>
 struct FastGeom {
-    static constexpr int L = fast_body_len(CL);
+    static constexpr int L = TIGHT ? CL : fast_body_len(CL);
     static constexpr int kPad = 2 * L - 2 * CL;        // zero-magnitude steps in front of the lead-in
     static constexpr int kRowBytes = 2 * L;            // one body's IQ bytes per chain
     static constexpr int kRowUnits = kRowBytes / 16;   // odd: conflict-free LDS.128
@@ -153,7 +156,7 @@ struct FastGeom {
     // the three non-sequential adds of two neighbouring steps as packed FADD2 (one issue slot for two
     // IEEE adds); rings longer than 88 run out of registers with the pair constraints and stay scalar
     static constexpr bool kPacked = (L <= 88);
-    static_assert(L % 8 == 0 && (kRowUnits & 1) == 1 && L > CL && kPad >= 0 && kPad < L, "bad body length");
+    static_assert(L % 8 == 0 && (kRowUnits & 1) == 1 && L >= CL && kPad >= 0 && kPad < L, "bad body length");
     static_assert(CL % 2 == 0, "the packed-pair rings need an even chip length");
 };
 
@@ -168,7 +171,7 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
                   const float* __restrict__ lut_g, uint32_t* __restrict__ plane_out, long long nblocks, int BS,
                   unsigned long long* __restrict__ tile_counter) {
     constexpr bool HYBRID = (VAR & 1) != 0;
-    using G = FastGeom<CL, (VAR & 2) ? 3 : 2>;
+    using G = FastGeom<CL, (VAR & 2) ? 3 : 2, (VAR & 4) != 0>;
     constexpr int L = G::L;
     extern __shared__ __align__(128) uint8_t fast_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -188,10 +191,10 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
     }
 
     // ---- prologue: LUT [v][lane] + zero column, barriers ----
-    for (int i = threadIdx.x; i < 256 * 33; i += WARPS * 32) {
-        const int v = i / 33, l = i % 33;
-        const float x = (l < 32) ? lut_g[v] : 0.0f;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_base + v * 256 + l * 4), "f"(x) : "memory");
+    for (int v = warp; v < 256; v += WARPS) {   // row v: the value in the 32 lane columns, 0.0 in column 32
+        const float x = lut_g[v];
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_base + v * 256 + lane * 4), "f"(x) : "memory");
+        if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_base + v * 256 + 128), "f"(0.0f) : "memory");
     }
     if (lane == 0) {
 #pragma unroll
@@ -208,12 +211,20 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
     const uint32_t row = stage0 + lane * G::kRowBytes;
     const bool have_hist = hist_valid >= 2 * L;      // hist_valid is 0 or >= BlockSize
     uint32_t phases = 0;  // bit s = parity to wait for on stage s
+    int st = 0;           // stage of the next body (runs on across work tiles)
+    bool ready = false;   // the next body's stage was seen complete
+    int npref = 0;        // leading bodies of this work tile that were already issued during the previous one
 
-    for (;;) {
-        unsigned long long tile = 0;
-        if (lane == 0) tile = atomicAdd(tile_counter, 1ull);
-        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
-        if ((long long)tile >= ntiles) break;
+    // Work tiles are claimed one ahead: the id of the NEXT tile is asked for when a tile starts and is known long
+    // before the tile's last bodies, which refill the staging ring with the next tile's first bodies instead of
+    // letting it drain -- a warp pays the TMA latency once, not once per tile.
+    unsigned long long tile = 0;
+    if (lane == 0) tile = atomicAdd(tile_counter, 1ull);
+    tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+    while ((long long)tile < ntiles) {
+        unsigned long long next_raw = 0, next_tile = ~0ull;
+        int npref_next = 0;
+        if (lane == 0) next_raw = atomicAdd(tile_counter, 1ull);  // consumed after the lead-in bodies
 
         long long b = (long long)tile * 32 + lane;
         const bool live = b < nblocks;
@@ -244,21 +255,30 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
             ow0 = ow1; ow1 = ow2; ow2 = o;
             wi++;
         };
-        int st = 0;  // stage of body t = t % kStages
-        bool ready = false;  // the next body's stage was seen complete
 
         auto run_tile = [&](auto lc_tag) {
             constexpr bool kLaneCopies = decltype(lc_tag)::value;
+            // one [32 rows][2L bytes] box: body tb of work tile tl
+            auto issue_box = [&](unsigned long long tl, int tb, int stage) {
+                if (lane == 0) {
+                    const uint32_t bar = bar0 + stage * 8;
+                    mbar_arrive_expect_tx(bar, 32u * G::kRowBytes);
+                    const int x = (tb < 2) ? 2 * BS - 2 * G::kRowBytes + tb * G::kRowBytes : (tb - 2) * G::kRowBytes;
+                    const int y = (int)(tl * 32) - (tb < 2 ? 1 : 0);
+                    tma_load_2d(stage0 + stage * G::kStageBytes, &iq_map, x, y, bar);
+                }
+            };
             auto issue = [&](int t, int stage) {
-                if (t >= nbody) return;
+                if (t >= nbody) {   // past the end of this tile: the next tile's first bodies (never the call's first tile)
+                    if ((long long)next_tile < ntiles) {
+                        issue_box(next_tile, t - nbody, stage);
+                        npref_next++;
+                    }
+                    return;
+                }
                 const uint32_t bar = bar0 + stage * 8;
                 if constexpr (!kLaneCopies) {
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(bar, 32u * G::kRowBytes);
-                        const int x = (t < 2) ? 2 * BS - 2 * G::kRowBytes + t * G::kRowBytes : (t - 2) * G::kRowBytes;
-                        const int y = (int)(tile * 32) - (t < 2 ? 1 : 0);
-                        tma_load_2d(stage0 + stage * G::kStageBytes, &iq_map, x, y, bar);
-                    }
+                    issue_box(tile, t, stage);
                 } else {
                     // stream byte offset of body t relative to the block start: (t - 2) * 2L
                     const long long off = (long long)(t - 2) * G::kRowBytes;
@@ -390,15 +410,19 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
                 }
             };
 #pragma unroll
-            for (int s = 0; s < G::kStages; s++) issue(s, s);
+            for (int s = 0; s < G::kStages; s++)
+                if (s >= npref) issue(s, (st + s) % G::kStages);
             body(std::integral_constant<int, 0>{}, 0);
             body(std::integral_constant<int, 1>{}, 1);
+            next_tile = __shfl_sync(0xFFFFFFFFu, next_raw, 0);
 #pragma unroll 1
             for (int t = 2; t < nbody; t++) body(std::integral_constant<int, 2>{}, t);
         };
         if (tile == 0) run_tile(std::true_type{});
         else run_tile(std::false_type{});
         __syncwarp();
+        npref = npref_next;
+        tile = next_tile;
     }
 }
 
@@ -496,7 +520,7 @@ int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_sample
                          unsigned long long* tile_counter, cudaStream_t st, int* w_out, int* var_out) {
     if (w_out) *w_out = W;
     if (var_out) *var_out = VAR;
-    using G = FastGeom<CL, (VAR & 2) ? 3 : 2>;
+    using G = FastGeom<CL, (VAR & 2) ? 3 : 2, (VAR & 4) != 0>;
     auto kern = demod_fast_kernel<CL, W, VAR>;
     const int smem = fast_smem_bytes<G>(W, dynamic_smem_base());
     if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
@@ -571,12 +595,18 @@ inline int launch_demod_fast(int variant, int warps, const uint8_t* iq, const ui
             if (seven || warps == 7) return launch_demod_fast_cw<N, 7>(ERT_FAST_ARGS);           \
         }                                                                                        \
         return launch_demod_fast_cw<N, fast_warps<N>()>(ERT_FAST_ARGS);
-    // tuning knob (ERTGPU_FAST_WARPS): other resident-warp counts for the headline chip length
-    if (variant == 72 && warps == 108) return launch_demod_fast_cw<72, 8, 1>(ERT_FAST_ARGS);  // 100 + W: hybrid magnitude
-    if (variant == 72 && warps == 208) return launch_demod_fast_cw<72, 8, 2>(ERT_FAST_ARGS);  // 200 + W: 3-stage ring
-    if (variant == 72 && warps == 8) return launch_demod_fast_cw<72, 8>(ERT_FAST_ARGS);
-    if (variant == 72 && warps == 6) return launch_demod_fast_cw<72, 6>(ERT_FAST_ARGS);
-    if (variant == 72 && warps == 4) return launch_demod_fast_cw<72, 4>(ERT_FAST_ARGS);
+    // tuning knobs for the headline chip length: ERTGPU_FAST_WARPS = 100 * VAR + W  (W resident warps;
+    // VAR bit 0 = hybrid magnitude, bit 1 = 3-stage staging ring, bit 2 = tight ring L = CL)
+    if (variant == 72 && warps >= 4) {
+        const int w = warps % 100, var = warps / 100;
+#define ERT_FAST_TUNE(W_, V_) if (w == W_ && var == V_) return launch_demod_fast_cw<72, W_, V_>(ERT_FAST_ARGS);
+        ERT_FAST_TUNE(8, 1)
+        ERT_FAST_TUNE(7, 0) ERT_FAST_TUNE(8, 0) ERT_FAST_TUNE(6, 0) ERT_FAST_TUNE(4, 0)
+        ERT_FAST_TUNE(7, 2) ERT_FAST_TUNE(8, 2)
+        ERT_FAST_TUNE(7, 4) ERT_FAST_TUNE(8, 4)
+        ERT_FAST_TUNE(7, 6) ERT_FAST_TUNE(8, 6)
+#undef ERT_FAST_TUNE
+    }
     switch (variant) {
         ERT_FAST_CASE(32) ERT_FAST_CASE(40) ERT_FAST_CASE(48) ERT_FAST_CASE(56) ERT_FAST_CASE(64)
         ERT_FAST_CASE(72) ERT_FAST_CASE(78) ERT_FAST_CASE(80) ERT_FAST_CASE(88) ERT_FAST_CASE(96)

@@ -51,6 +51,19 @@ struct RawHit {
     int32_t pad;
 };
 
+// One word of 32 consecutive start positions with at least one hit: what Search hands to Slice.
+// Start gw*32 + k (k counted from the MSB of `mask`) is a hit iff bit 31-k of mask is set; its RawHit
+// (and, for r900, its payload digits) sits at index slot + (number of set bits above it).
+struct HitWord {
+    unsigned long long gw;    // call-relative word of starts
+    unsigned long long slot;  // index of the word's first RawHit
+    uint32_t mask;
+    int32_t preamble_id;
+};
+
+// counters of one pipeline (unsigned long long each)
+enum { kCntHits = 0, kCntOut = 1, kCntValid = 2, kCntTile = 3, kCntWords = 4, kCntN = 8 };
+
 // Plane bit order: stream bit g lives in word g>>5 at bit position 31-(g&31)
 // (MSB first, like the reference's packed bytes, decode.go:259-265).
 __device__ __forceinline__ uint32_t plane_bit(const uint32_t* __restrict__ plane, long long pos) {

@@ -62,6 +62,7 @@ struct ertgpu_handle {
     size_t h_stage_bytes = 0;
     std::string kernels;                        // instantiations launched by the last pipeline
     RawHit* d_hits = nullptr;
+    HitWord* d_words = nullptr;       // words of starts that hold a hit (what Slice works from)
     uint8_t* d_digits = nullptr;
     int* d_block_slot = nullptr;      // r900: scratch slot of each block of the call (-1 none)
     int* d_slot_block = nullptr;
@@ -70,7 +71,7 @@ struct ertgpu_handle {
     int r900_slots = 0, r900_span = 0;
     ertgpu_candidate* d_out = nullptr;
     unsigned long long cand_cap = 0;
-    unsigned long long* d_counters = nullptr;  // [0]=hits [1]=out [2]=valid [3]=demod work-tile counter
+    unsigned long long* d_counters = nullptr;  // kCntHits, kCntOut, kCntValid, kCntTile (demod work tiles), kCntWords
     unsigned long long* h_counters = nullptr;  // pinned mirror
     float* d_tap = nullptr;                    // scratch for taps
     size_t tap_floats = 0;
@@ -194,6 +195,7 @@ void free_device(ertgpu_handle* h) {
     dfree(h->d_crc);
     dfree(h->d_crc_pos);
     dfree(h->d_hits);
+    dfree(h->d_words);
     dfree(h->d_digits);
     dfree(h->d_block_slot);
     dfree(h->d_slot_block);
@@ -239,7 +241,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     const long long p0 = (long long)c.hist_words * 32 - c.PKL;
     h->launches = 0;
 
-    CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, kCntN * sizeof(unsigned long long), st));
     if (h->fresh) {  // Quantized starts as zeros (decode.go:145); only the history in front of the call is read
         CUDA_TRY(h, cudaMemsetAsync(plane, 0, (size_t)c.hist_words * sizeof(uint32_t), st));
         h->fresh = false;
@@ -258,7 +260,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     if (h->demod_variant != 0) {
         int w_used = 0, var_used = 0;
         int rc = launch_demod_fast(h->demod_variant, h->demod_warps, d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut,
-                                   plane + c.hist_words, nblocks, c.BS, h->d_counters + 3, st, &w_used, &var_used);
+                                   plane + c.hist_words, nblocks, c.BS, h->d_counters + kCntTile, st, &w_used, &var_used);
         if (rc != 0) return fail(h, ERTGPU_ECUDA, "demod_fast launch failed: %s", cudaGetErrorString((cudaError_t)rc));
         snprintf(kname, sizeof(kname), "demod_fast_kernel<%d,%d,%d>", h->demod_variant, w_used, var_used);
         h->kernels = kname;
@@ -294,7 +296,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
         static OncePerDevice once;                                                                               \
         if (once.first(h->device))                                                                               \
             CUDA_TRY(h, cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * kSlideMaxLoad + 4))); \
-        K<<<grid, kSlideThreads, smem, st>>>(plane, sl, h->d_hits, h->cand_cap, h->d_counters);                  \
+        K<<<grid, kSlideThreads, smem, st>>>(plane, sl, h->d_hits, h->d_words, h->cand_cap, h->d_counters);      \
     } while (0)
 #define ERT_SLIDE(N, ...)                                                                    \
     do {                                                                                     \
@@ -326,7 +328,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
             unsigned grid = (unsigned)std::min<long long>(tiles, 148 * 4);
             if (grid < 1) grid = 1;
             const int mode = search_mode(c, p0);
-#define ERT_SEARCH(N, M) search_kernel<N, M><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->cand_cap, h->d_counters)
+#define ERT_SEARCH(N, M) search_kernel<N, M><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->d_words, h->cand_cap, h->d_counters)
 #define ERT_SEARCH_N(N) do { if (mode == 1) ERT_SEARCH(N, 1); else if (mode == 2) ERT_SEARCH(N, 2); else ERT_SEARCH(N, 0); } while (0)
             switch (c.npre) {
                 case 1: ERT_SEARCH_N(1); break;
@@ -340,7 +342,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
             const int nthr = 256;
             long long blocks = std::min<long long>((nwords + nthr - 1) / nthr, 148 * 16);
             if (blocks < 1) blocks = 1;
-            search_generic_kernel<<<(unsigned)blocks, nthr, 0, st>>>(plane, p0, nwords, c, h->d_hits, h->cand_cap, h->d_counters);
+            search_generic_kernel<<<(unsigned)blocks, nthr, 0, st>>>(plane, p0, nwords, c, h->d_hits, h->d_words, h->cand_cap, h->d_counters);
         }
         CUDA_TRY(h, cudaGetLastError());
         h->launches++;
@@ -376,20 +378,26 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
         digits = h->d_digits;
     }
 
-    // 4. slice + integrity screens
-    extract_kernel<<<148 * 8, kExtractWarps * 32, 0, st>>>(plane, p0, c, h->d_hits, h->cand_cap, h->d_counters, h->d_crc, h->d_crc_pos, h->gf,
-                                           digits, h->block_counter, flags, h->d_out, h->cand_cap,
-                                           h->d_counters + 1, h->d_counters + 2);
-    CUDA_TRY(h, cudaGetLastError());
-    h->launches++;
+    // 4. slice + integrity screens, one warp per word of starts with a hit; the same kernel carries the history to
+    //    the other plane / history buffers (both only read what the earlier kernels wrote)
+    {
+        CarryArgs ca;
+        ca.plane_src = plane; ca.plane_dst = plane_next; ca.src_offset_words = nwords; ca.hist_words = c.hist_words;
+        ca.iq = d_iq; ca.hist_src = hist; ca.hist_dst = hist_next; ca.hist_samples = c.hist_samples;
+        ca.nsamples = nblocks * c.BS;
+        const unsigned grid = (unsigned)h->sm_count * 4;
+        if (c.PK <= 128)
+            extract_words_kernel<4><<<grid, kExtractWarps * 32, 0, st>>>(plane, p0, c, h->d_words, h->cand_cap, h->d_crc, h->gf, digits,
+                                                                    h->block_counter, flags, h->d_out, h->cand_cap, h->d_counters, ca);
+        else
+            extract_words_kernel<(ERTGPU_MAX_PACKET_BYTES * 8 + 31) / 32><<<grid, kExtractWarps * 32, 0, st>>>(
+                plane, p0, c, h->d_words, h->cand_cap, h->d_crc, h->gf, digits, h->block_counter, flags, h->d_out, h->cand_cap,
+                h->d_counters, ca);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches++;
+    }
 
     if (tm) CUDA_TRY(h, cudaEventRecord(h->ev_stage[3], st));
-    // 5. carry history to the other buffers
-    carry_kernel<<<64, 256, 0, st>>>(plane, plane_next, nwords, c.hist_words, d_iq, hist, hist_next, c.hist_samples,
-                                     nblocks * c.BS);
-    CUDA_TRY(h, cudaGetLastError());
-    h->launches++;
-
     if (tm) CUDA_TRY(h, cudaEventRecord(h->ev_stage[4], st));
     h->stage_valid = tm;
     CUDA_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -718,6 +726,7 @@ static int allocate_impl(ertgpu_handle* h, int32_t device, int64_t max_blocks_pe
         CUDA_TRY(h, cudaMemset(h->d_hist[k], 0, (size_t)d.hist_samples * 2 + 16));
     }
     CUDA_TRY(h, cudaMalloc(&h->d_hits, h->cand_cap * sizeof(RawHit)));
+    CUDA_TRY(h, cudaMalloc(&h->d_words, h->cand_cap * sizeof(HitWord)));
     CUDA_TRY(h, cudaMalloc(&h->d_out, h->cand_cap * sizeof(ertgpu_candidate)));
     if (h->has_r900) {
         CUDA_TRY(h, cudaMalloc(&h->d_digits, h->cand_cap * ERTGPU_R900_DIGITS));
@@ -737,13 +746,13 @@ static int allocate_impl(ertgpu_handle* h, int32_t device, int64_t max_blocks_pe
         CUDA_TRY(h, cudaMalloc(&h->d_slot_count, sizeof(unsigned int)));
         CUDA_TRY(h, cudaMalloc(&h->d_r900_scratch, (size_t)h->r900_slots * (size_t)h->r900_span * sizeof(float)));
     }
-    CUDA_TRY(h, cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)));
-    CUDA_TRY(h, cudaHostAlloc(&h->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    CUDA_TRY(h, cudaMalloc(&h->d_counters, kCntN * sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaHostAlloc(&h->h_counters, kCntN * sizeof(unsigned long long), cudaHostAllocDefault));
     h->tap_floats = (size_t)std::max(d.BS + d.SL, d.BUF) * 2 + 16;
     CUDA_TRY(h, cudaMalloc(&h->d_tap, h->tap_floats * sizeof(float)));
 
     h->demod_variant = demod_fast_variant(d.CL, d.BS);
-    if (const char* e = getenv("ERTGPU_FAST_WARPS")) h->demod_warps = atoi(e);
+    if (const char* e = getenv("ERTGPU_FAST_WARPS")) h->demod_warps = atoi(e);   // 100 * VAR + W, see launch_demod_fast
     if (const char* e = getenv("ERTGPU_SEARCH_LEGACY")) h->search_legacy = atoi(e) != 0;
     if (const char* e = getenv("ERTGPU_R900_CHAIN")) h->r900_chain_shfl = strcmp(e, "shfl") == 0;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);

@@ -55,6 +55,36 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     return v;
 }
 
+// A word of starts with surviving bits m (MSB = first start of the word): reserve its RawHits (one reservation
+// per word: same-address atomics serialise in L2) and file the word itself for Slice.  counters = the pipeline's
+// counter block (kCntHits, kCntWords).
+__device__ __forceinline__ void emit_hit_word(uint32_t m, long long gw, int p, RawHit* __restrict__ hits,
+                                              HitWord* __restrict__ words, unsigned long long hit_cap,
+                                              unsigned long long* __restrict__ counters) {
+    unsigned long long slot = atomicAdd(&counters[kCntHits], (unsigned long long)__popc(m));
+    const unsigned long long wslot = atomicAdd(&counters[kCntWords], 1ull);
+    if (wslot < hit_cap) {
+        HitWord w;
+        w.gw = (unsigned long long)gw;
+        w.slot = slot;
+        w.mask = m;
+        w.preamble_id = p;
+        words[wslot] = w;
+    }
+    while (m) {
+        const int lead = __clz(m);  // MSB = first start of the word
+        m &= ~(0x80000000u >> lead);
+        if (slot < hit_cap) {
+            RawHit h;
+            h.s = (unsigned long long)((gw << 5) + lead);
+            h.preamble_id = p;
+            h.pad = 0;
+            hits[slot] = h;
+        }
+        slot++;
+    }
+}
+
 // The plane's first start lies in the first 4 words (p0 < 128), so tile t starts at plane word t*kSearchTile:
 // 16-byte aligned, fetched with one cp.async.bulk per tile into a 2-stage ring (the plane is
 // allocated with kSearchTile + kSearchMaxHalo words of slack so the last tile can over-read).
@@ -63,7 +93,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 // Every chip length the reference CLI accepts gives MODE 1 or 2 (SL = 2*CL, CL a multiple of 8).
 template <int NPRE, int MODE>
 __global__ void __launch_bounds__(kSearchThreads)
-search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __restrict__ hits,
+search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __restrict__ hits, HitWord* __restrict__ words,
               unsigned long long hit_cap, unsigned long long* __restrict__ hit_count) {
     __shared__ __align__(128) uint32_t buf[2][kSearchTile + kSearchMaxHalo];
     __shared__ __align__(8) unsigned long long bars[2];
@@ -117,20 +147,7 @@ search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __res
                     mm &= x ^ sp.inv[p][k];
                 }
                 if (mm == 0) continue;
-                // one reservation per word of starts (same-address atomics serialise in L2)
-                unsigned long long slot = atomicAdd(hit_count, (unsigned long long)__popc(mm));
-                while (mm) {
-                    const int lead = __clz(mm);  // MSB = first start of the word
-                    mm &= ~(0x80000000u >> lead);
-                    if (slot < hit_cap) {
-                        RawHit h;
-                        h.s = (unsigned long long)(((t0 + j) << 5) + lead);
-                        h.preamble_id = p;
-                        h.pad = 0;
-                        hits[slot] = h;
-                    }
-                    slot++;
-                }
+                emit_hit_word(mm, t0 + j, p, hits, words, hit_cap, hit_count);
             }
         }
         __syncthreads();  // everyone is done with buf[st]: it may be refilled next iteration
@@ -174,7 +191,7 @@ struct SlideParams {
 // A word of starts that survived the probe: test bits kSlideProbe .. nbits-1 from shared memory and emit.
 // wa = shared address of the word's bit-0 window, gw = call-relative word of starts.
 __device__ __noinline__ void slide_finish(const SlideParams* sp, int p, uint32_t wa, uint32_t m, long long gw,
-                                          RawHit* __restrict__ hits, unsigned long long hit_cap,
+                                          RawHit* __restrict__ hits, HitWord* __restrict__ words, unsigned long long hit_cap,
                                           unsigned long long* __restrict__ hit_count) {
     const int nb = sp->nbits[p];
     for (int k = kSlideProbe; k < nb && m; k++) {
@@ -189,20 +206,7 @@ __device__ __noinline__ void slide_finish(const SlideParams* sp, int p, uint32_t
         m &= x ^ sp->inv[p][k];
     }
     if (m == 0 || gw >= sp->nwords) return;
-    // one reservation per word of starts (same-address atomics serialise in L2)
-    unsigned long long slot = atomicAdd(hit_count, (unsigned long long)__popc(m));
-    while (m) {
-        const int lead = __clz(m);  // MSB = first start of the word
-        m &= ~(0x80000000u >> lead);
-        if (slot < hit_cap) {
-            RawHit h;
-            h.s = (unsigned long long)((gw << 5) + lead);
-            h.preamble_id = p;
-            h.pad = 0;
-            hits[slot] = h;
-        }
-        slot++;
-    }
+    emit_hit_word(m, gw, p, hits, words, hit_cap, hit_count);
 }
 
 // PAT: the first 16 preamble bits as a compile-time constant (bit 15 = preamble bit 0) for single-preamble
@@ -211,7 +215,8 @@ __device__ __noinline__ void slide_finish(const SlideParams* sp, int p, uint32_t
 template <int NPRE, bool HALF, uint32_t PAT = kSlideRuntimePat>
 __global__ void __launch_bounds__(kSlideThreads)
 search_slide_kernel(const uint32_t* __restrict__ plane, const __grid_constant__ SlideParams sp,
-                    RawHit* __restrict__ hits, unsigned long long hit_cap, unsigned long long* __restrict__ hit_count) {
+                    RawHit* __restrict__ hits, HitWord* __restrict__ words, unsigned long long hit_cap,
+                    unsigned long long* __restrict__ hit_count) {
     extern __shared__ __align__(128) uint32_t slide_smem[];  // [2][load_words] then two mbarriers
     const uint32_t buf0 = smem_u32(slide_smem);
     const uint32_t stage_bytes = (uint32_t)sp.load_words * 4u;
@@ -284,7 +289,7 @@ search_slide_kernel(const uint32_t* __restrict__ plane, const __grid_constant__ 
                         const uint32_t m = me & mo;
                         if (m != 0) {
                             const int s = rep * kSlideRing + i;
-                            slide_finish(&sp, p, a0 + (uint32_t)s * step, m, t0 + j0 + (long long)q * s, hits, hit_cap,
+                            slide_finish(&sp, p, a0 + (uint32_t)s * step, m, t0 + j0 + (long long)q * s, hits, words, hit_cap,
                                          hit_count);
                         }
                     }
@@ -368,7 +373,8 @@ __device__ __forceinline__ uint32_t plane_window2(const uint32_t* __restrict__ p
 
 __global__ void __launch_bounds__(256)
 search_generic_kernel(const uint32_t* __restrict__ plane, long long p0, long long nwords, DevCfg cfg,
-                      RawHit* __restrict__ hits, unsigned long long hit_cap, unsigned long long* __restrict__ hit_count) {
+                      RawHit* __restrict__ hits, HitWord* __restrict__ words, unsigned long long hit_cap,
+                      unsigned long long* __restrict__ hit_count) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride) {
         const long long base = p0 + (w << 5);
@@ -379,18 +385,7 @@ search_generic_kernel(const uint32_t* __restrict__ plane, long long p0, long lon
                 const uint32_t x = plane_window2(plane, base + (long long)k * cfg.SL);
                 m &= cfg.pre_bits[p][k] ? x : ~x;
             }
-            while (m) {
-                const int lead = __clz(m);
-                m &= ~(0x80000000u >> lead);
-                const unsigned long long slot = atomicAdd(hit_count, 1ull);
-                if (slot < hit_cap) {
-                    RawHit h;
-                    h.s = (unsigned long long)((w << 5) + lead);
-                    h.preamble_id = p;
-                    h.pad = 0;
-                    hits[slot] = h;
-                }
-            }
+            if (m) emit_hit_word(m, w, p, hits, words, hit_cap, hit_count);
         }
     }
 }
@@ -402,114 +397,139 @@ struct Gf32 {
 };
 
 constexpr int kExtractWarps = 8;
+constexpr int kExtractRowWords = 25;  // packet words per candidate row in shared memory: odd pitch, conflict free
 
-// One WARP per candidate (grid-stride over warps).  Lane l gathers packet symbols l, l+32, ...
-// (decode.go:363-366: bit p of the packet is stream bit start + p*SL); a ballot turns 32 symbols into
-// 4 packet bytes.  The warp then runs the screens of every parser filed under the candidate's preamble
-// (CRC-16 folded in parallel through per-position tables), and the 160-byte record is written by all lanes.
-// If `r900_digits` is non-null it holds, per raw hit, the 42 payload digits computed by
-// r900_replay_kernel.
-__global__ void __launch_bounds__(kExtractWarps * 32, 4)
-extract_kernel(const uint32_t* __restrict__ plane, long long p0, const __grid_constant__ DevCfg cfg,
-               const RawHit* __restrict__ hits,
-               unsigned long long hit_cap, const unsigned long long* __restrict__ hit_count,
-               const uint16_t* __restrict__ crc_tables, const uint16_t* __restrict__ crc_pos,
-               const __grid_constant__ Gf32 gf,  // __grid_constant__: indexed in place, no per-thread local copy
-               const uint8_t* __restrict__ r900_digits,
-               long long first_block, uint32_t flags, ertgpu_candidate* __restrict__ out,
-               unsigned long long out_cap, unsigned long long* __restrict__ out_count,
-               unsigned long long* __restrict__ valid_count) {
-    __shared__ __align__(16) ertgpu_candidate rec_s[kExtractWarps];
-    (void)crc_tables;  // the byte-serial tables are kept for reference; the screens use the per-position tables
+// 32 x 32 bit transpose across a warp, MSB-first on both sides: in = lane r's word, bit 31-k = element (r, k);
+// out = lane c's word, bit 31-r = element (r, c).  Five exchange steps of off-diagonal blocks (16 .. 1).
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t keep = (j == 16) ? 0xFFFF0000u : (j == 8) ? 0xFF00FF00u : (j == 4) ? 0xF0F0F0F0u
+                              : (j == 2) ? 0xCCCCCCCCu : 0xAAAAAAAAu;
+        const uint32_t partner = __shfl_xor_sync(0xFFFFFFFFu, x, j);
+        x = (lane & j) ? ((x & ~keep) | ((partner & ~keep) << j)) : ((x & keep) | ((partner & keep) >> j));
+    }
+    return x;
+}
+
+// Carry the last `hist_words` words of a call's plane to the front of the other plane, and the last
+// `hist_samples` IQ samples into the other history buffer (ping-pong: no overlap hazards).  Grid-stride work
+// done by the threads of the Slice kernel (the plane and the IQ bytes are read-only by then).
+struct CarryArgs {
+    const uint32_t* plane_src;
+    uint32_t* plane_dst;
+    long long src_offset_words;
+    int hist_words;
+    const uint8_t* iq;
+    const uint8_t* hist_src;
+    uint8_t* hist_dst;
+    int hist_samples;
+    long long nsamples;
+};
+__device__ __forceinline__ void carry_part(const CarryArgs& c, int i0, int stride) {
+    for (int i = i0; i < c.hist_words; i += stride) c.plane_dst[i] = c.plane_src[c.src_offset_words + i];
+    // hist_dst[k] (k in [0,hist_samples)) = sample (nsamples - hist_samples + k) relative to the call
+    for (int k = i0; k < c.hist_samples; k += stride) {
+        const long long j = c.nsamples - c.hist_samples + k;
+        uint16_t v;
+        if (j >= 0) v = reinterpret_cast<const uint16_t*>(c.iq)[j];
+        else v = reinterpret_cast<const uint16_t*>(c.hist_src)[c.hist_samples + j];
+        reinterpret_cast<uint16_t*>(c.hist_dst)[k] = v;
+    }
+}
+
+// Slice (decode.go:353-375) + the parsers' integrity screens, one WARP per word of starts that holds a hit.
+//  * gather: bit p of the packet that starts at s is plane bit base + s + p*SL, so the 32 starts of the word
+//    share their loads: lane r reads the 32-bit window of symbol 32*ch + r (one funnel shift of two words) and a
+//    warp transpose hands lane c the 32 symbols of start c.  Adjacent sample phases of one transmission (~70
+//    starts in a row pass the preamble test) cost one pass instead of 70.
+//  * screens: lane c runs the checks of every parser filed under the preamble on ITS packet (byte-serial table
+//    CRC, crc/crc.go:49-55, tables and packet rows in shared memory); the r900 syndrome check stays warp-parallel
+//    per candidate (few candidates, 31 symbols each).
+//  * records: one slot reservation per word; every lane writes its own 160-byte record with 16-byte stores.
+// KMAX: chunks of 32 symbols gathered (4 covers PacketSymbols <= 128: scm, scm+, r900).
+template <int KMAX>
+__global__ void __launch_bounds__(kExtractWarps * 32)
+extract_words_kernel(const uint32_t* __restrict__ plane, long long p0, const __grid_constant__ DevCfg cfg,
+                     const HitWord* __restrict__ words, unsigned long long word_cap,
+                     const uint16_t* __restrict__ crc_tables, const __grid_constant__ Gf32 gf,
+                     const uint8_t* __restrict__ r900_digits, long long first_block, uint32_t flags,
+                     ertgpu_candidate* __restrict__ out, unsigned long long out_cap,
+                     unsigned long long* __restrict__ counters, const __grid_constant__ CarryArgs carry) {
+    __shared__ uint16_t tab_s[ERTGPU_MAX_PROTOCOLS][256];
+    __shared__ uint32_t rows_s[kExtractWarps][32 * kExtractRowWords];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    ertgpu_candidate* rec = &rec_s[warp];
-    uint8_t* bytes = rec->bytes;
-    unsigned long long n = *hit_count;
-    if (n > hit_cap) n = hit_cap;
-    __shared__ unsigned long long base_s;
-    __shared__ uint32_t want_s[kExtractWarps];  // bit0: record is emitted, bit1: passed a screen
-    const unsigned long long cstride = (unsigned long long)gridDim.x * kExtractWarps;
-    // all warps of the CTA run the same number of rounds so that the slot reservation can be one
-    // atomic per CTA round (same-address atomics serialise in L2)
-    for (unsigned long long c0 = (unsigned long long)blockIdx.x * kExtractWarps; c0 < n; c0 += cstride) {
-        const unsigned long long c = c0 + warp;
-        const bool have = c < n;
-        RawHit h;
-        h.s = 0; h.preamble_id = 0; h.pad = 0;
-        if (have) h = hits[c];
-        if (have) {
-            const int nchunks = (cfg.PK + 31) >> 5;
-            // bit p of the packet is plane bit base + p*SL: 32-bit offsets from the word that holds the start
-            const long long base = p0 + (long long)h.s;
-            const uint32_t* __restrict__ pw = plane + (base >> 5);
-            const uint32_t bit0 = (uint32_t)(base & 31);
-            // issue all strided plane reads of a group first (independent loads overlap), then ballot
-            auto gather = [&](auto maxc) {
-                constexpr int kMax = decltype(maxc)::value;
-                uint32_t bit[kMax];
+    carry_part(carry, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    unsigned long long n = counters[kCntWords];
+    if (n > word_cap) n = word_cap;
+    if ((unsigned long long)blockIdx.x * kExtractWarps >= n) return;
+    for (int i = threadIdx.x; i < cfg.nproto * 256; i += blockDim.x) tab_s[i >> 8][i & 255] = crc_tables[i];
+    __syncthreads();
+    uint32_t* const row = &rows_s[warp][lane * kExtractRowWords];
+    const uint8_t* const rowb = reinterpret_cast<const uint8_t*>(row);
+    const int nchunks = (cfg.PK + 31) >> 5;
+    const int shift = bs_shift(cfg);
+    for (unsigned long long w = (unsigned long long)blockIdx.x * kExtractWarps + warp; w < n;
+         w += (unsigned long long)gridDim.x * kExtractWarps) {
+        const HitWord hw = words[w];
+        const long long base = p0 + (long long)(hw.gw << 5);
+        // ---- gather + transpose: row[ch] = symbols 32*ch .. 32*ch+31 of start `lane`, in packet byte order
 #pragma unroll
-                for (int ch = 0; ch < kMax; ch++) {
-                    const int sym = ch * 32 + lane;
-                    uint32_t bv = 0;
-                    if (ch < nchunks && sym < cfg.PK) {
-                        const uint32_t rel = bit0 + (uint32_t)sym * (uint32_t)cfg.SL;
-                        bv = (pw[rel >> 5] >> (31u - (rel & 31u))) & 1u;
-                    }
-                    bit[ch] = bv;
-                }
-#pragma unroll
-                for (int ch = 0; ch < kMax; ch++) {
-                    if (ch < nchunks) {
-                        const uint32_t v = __brev(__ballot_sync(0xFFFFFFFFu, bit[ch]));  // MSB = symbol 32*ch
-                        // bytes[] starts at a 4-byte boundary of the record: one word store per 32 symbols
-                        if (lane == 0 && ch * 4 < ERTGPU_MAX_PACKET_BYTES)
-                            reinterpret_cast<uint32_t*>(bytes)[ch] = __byte_perm(v, 0u, 0x0123);
-                    }
-                }
-            };
-            if (nchunks <= 4) gather(std::integral_constant<int, 4>{});
-            else gather(std::integral_constant<int, (ERTGPU_MAX_PACKET_BYTES * 8 + 31) / 32>{});
-            for (int q = nchunks * 4 + lane; q < ERTGPU_MAX_PACKET_BYTES; q += 32) bytes[q] = 0;
-            __syncwarp();
-            if (lane == 0) {
-                // a trailing partial byte holds its PK%8 bits in the LOW bits, like d.pkt after PK%8 shifts
-                // of a zeroed buffer (decode.go:363-366)
-                if (cfg.PK & 7) bytes[cfg.PK >> 3] = (uint8_t)(bytes[cfg.PK >> 3] >> (8 - (cfg.PK & 7)));
-                for (int q = cfg.packet_bytes; q < nchunks * 4 && q < ERTGPU_MAX_PACKET_BYTES; q++) bytes[q] = 0;
+        for (int ch = 0; ch < KMAX; ch++) {
+            uint32_t win = 0;
+            const int sym = ch * 32 + lane;
+            if (ch < nchunks && sym < cfg.PK) {
+                const long long pos = base + (long long)sym * cfg.SL;
+                const uint32_t* pw = plane + (pos >> 5);
+                win = __funnelshift_l(pw[1], pw[0], (int)(pos & 31));
             }
-            __syncwarp();
-            // Integrity screens of every parser filed under this preamble.  The table CRC of crc/crc.go:49-55 is
-            // linear over GF(2): CRC(init, M) = CRC(init, 0^n) xor XOR_p T_p[M[p]], T_p[v] = CRC(0, v at position p).
-            // Each lane folds the bytes p = lane, lane+32, ... through the per-position tables and the warp XORs the
-            // partial results: a 88-byte IDM check costs 3 lookups per lane instead of 88 dependent ones.
-            uint32_t mask = 0;
-            const bool has_dig = r900_digits != nullptr && cfg.pre_has_r900[h.preamble_id];
-            const uint8_t* dig = has_dig ? r900_digits + c * ERTGPU_R900_DIGITS : nullptr;
-            for (int i = 0; i < cfg.nproto; i++) {
-                const DevProto& pr = cfg.proto[i];
-                if (pr.preamble_id != h.preamble_id) continue;
-                bool ok = false;
-                if (pr.check_kind == ERTGPU_CHECK_NONE) {
-                    ok = true;
-                } else if (pr.check_kind == ERTGPU_CHECK_CRC16 || pr.check_kind == ERTGPU_CHECK_IDM) {
-                    uint32_t part = 0, part2 = 0;
-                    for (int q = lane; q < pr.pos_n; q += 32)
-                        part ^= crc_pos[(size_t)(pr.pos_base + q) * 256 + bytes[pr.crc_from + q]];
-                    if (pr.check_kind == ERTGPU_CHECK_IDM && lane < 6) {   // Bytes[9:13] + Bytes[88:90], idm.go:82-87
-                        const int bi = lane < 4 ? 9 + lane : 84 + lane;
-                        part2 = crc_pos[(size_t)(pr.pos2_base + lane) * 256 + bytes[bi]];
-                    }
+            if (ch < nchunks) row[ch] = __byte_perm(warp_transpose32(win, lane), 0u, 0x0123);
+            else row[ch] = 0u;
+        }
+        for (int ch = KMAX; ch < ERTGPU_MAX_PACKET_BYTES / 4; ch++) row[ch] = 0u;
+        if (cfg.PK & 7) {
+            // a trailing partial byte holds its PK%8 bits in the LOW bits, like d.pkt after PK%8 shifts of a zeroed
+            // buffer (decode.go:363-366)
+            uint8_t* rb = reinterpret_cast<uint8_t*>(row);
+            rb[cfg.PK >> 3] = (uint8_t)(rb[cfg.PK >> 3] >> (8 - (cfg.PK & 7)));
+        }
+        __syncwarp();
+        const bool active = (hw.mask >> (31 - lane)) & 1u;
+        const int rank = __popc(hw.mask >> (31 - lane)) - 1;   // set bits above this lane's = index among the word's hits
+        const bool has_dig = r900_digits != nullptr && cfg.pre_has_r900[hw.preamble_id];
+        // ---- screens
+        uint32_t mask = 0;
+        for (int i = 0; i < cfg.nproto; i++) {
+            const DevProto& pr = cfg.proto[i];
+            if (pr.preamble_id != hw.preamble_id) continue;
+            bool ok = false;
+            if (pr.check_kind == ERTGPU_CHECK_NONE) {
+                ok = true;
+            } else if (pr.check_kind == ERTGPU_CHECK_CRC16 || pr.check_kind == ERTGPU_CHECK_IDM) {
+                const uint16_t* tb = tab_s[pr.table];
+                uint32_t crc = pr.crc_init;
+                if (active) {
+                    for (int q = pr.crc_from; q < pr.crc_to; q++) crc = ((crc << 8) & 0xFFFFu) ^ tb[(crc >> 8) ^ rowb[q]];
+                    ok = crc == pr.crc_residue;
+                    if (ok && pr.check_kind == ERTGPU_CHECK_IDM) {   // Bytes[9:13] + Bytes[88:90], idm.go:82-87
+                        crc = pr.crc_init;
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) {
-                        part ^= __shfl_xor_sync(0xFFFFFFFFu, part, d);
-                        part2 ^= __shfl_xor_sync(0xFFFFFFFFu, part2, d);
+                        for (int q = 0; q < 6; q++) crc = ((crc << 8) & 0xFFFFu) ^ tb[(crc >> 8) ^ rowb[q < 4 ? 9 + q : 84 + q]];
+                        ok = crc == pr.crc_residue;
                     }
-                    ok = (uint16_t)(part ^ pr.pos_k) == pr.crc_residue;
-                    if (pr.check_kind == ERTGPU_CHECK_IDM) ok = ok && (uint16_t)(part2 ^ pr.pos2_k) == pr.crc_residue;
-                } else if (pr.check_kind == ERTGPU_CHECK_R900 && dig) {
-                    // r900.go:199-221 across the warp: lane q holds message symbol q of the 31-symbol RS word
-                    // (16 data symbols, 10 zeros, 5 parity symbols; each symbol = two base-6 digits).  The Horner
-                    // evaluation of gf.go:163-169 at root a^(29+s) equals XOR_q msg[q] * root^(30-q).
+                }
+            } else if (pr.check_kind == ERTGPU_CHECK_R900 && has_dig) {
+                // r900.go:199-221 across the warp, one candidate of the word at a time: lane q holds message symbol q of
+                // the 31-symbol RS word (16 data symbols, 10 zeros, 5 parity symbols; each symbol = two base-6 digits).
+                // The Horner evaluation of gf.go:163-169 at root a^(29+s) equals XOR_q msg[q] * root^(30-q).
+                uint32_t okbits = 0;
+                uint32_t m = hw.mask;
+                unsigned long long c = hw.slot;
+                while (m) {   // warp-uniform
+                    const int lead = __clz(m);
+                    m &= ~(0x80000000u >> lead);
+                    const uint8_t* dig = r900_digits + c * ERTGPU_R900_DIGITS;
+                    c++;
                     int sym = 0;
                     bool bad = false;
                     if (lane < 31 && (lane < 16 || lane >= 26)) {
@@ -517,7 +537,7 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, const __grid_co
                         sym = dig[2 * k] * 6 + dig[2 * k + 1];
                         bad = sym > 31;
                     }
-                    ok = __ballot_sync(0xFFFFFFFFu, bad) == 0;
+                    bool okc = __ballot_sync(0xFFFFFFFFu, bad) == 0;
                     uint32_t synd = 0;  // 5 syndromes x 5 bits packed
                     if (sym > 0 && sym < 32) {
                         const int lg = gf.log[sym];
@@ -529,46 +549,46 @@ extract_kernel(const uint32_t* __restrict__ plane, long long p0, const __grid_co
                     }
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) synd ^= __shfl_xor_sync(0xFFFFFFFFu, synd, d);
-                    ok = ok && synd == 0;
+                    okc = okc && synd == 0;
+                    if (okc) okbits |= 0x80000000u >> lead;
                 }
-                if (ok) mask |= 1u << i;
+                ok = active && ((okbits >> (31 - lane)) & 1u);
             }
-            if (lane == 0) {
-                rec->block = first_block + (long long)(h.s >> bs_shift(cfg));
-                rec->idx = (int32_t)(h.s & (unsigned long long)(cfg.BS - 1));
-                rec->preamble_id = h.preamble_id;
-                rec->check_mask = mask;
-                rec->flags = has_dig ? ERTGPU_CAND_HAS_R900 : 0u;
-                rec->pad[0] = rec->pad[1] = 0;
-                want_s[warp] = ((mask || !(flags & ERTGPU_DECODE_ONLY_VALID)) ? 1u : 0u) | (mask ? 2u : 0u);
-            }
-            {   // the digits are copied by all lanes (lane 0 only reads them above)
-                const bool has_dig = r900_digits != nullptr && cfg.pre_has_r900[h.preamble_id];
-                for (int q = lane; q < ERTGPU_R900_DIGITS; q += 32)
-                    rec->r900_digits[q] = has_dig ? r900_digits[c * ERTGPU_R900_DIGITS + q] : (uint8_t)0;
-            }
-        } else if (lane == 0) {
-            want_s[warp] = 0;
+            if (ok) mask |= 1u << i;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned nout = 0, nvalid = 0;
-            for (int q = 0; q < kExtractWarps; q++) { nout += want_s[q] & 1u; nvalid += (want_s[q] >> 1) & 1u; }
-            if (nvalid) atomicAdd(valid_count, (unsigned long long)nvalid);
-            base_s = nout ? atomicAdd(out_count, (unsigned long long)nout) : 0ull;
+        // ---- records
+        const bool emit = active && (mask != 0 || !(flags & ERTGPU_DECODE_ONLY_VALID));
+        const uint32_t emit_b = __ballot_sync(0xFFFFFFFFu, emit);
+        const uint32_t valid_b = __ballot_sync(0xFFFFFFFFu, active && mask != 0);
+        unsigned long long slot0 = 0;
+        if (lane == 0) {
+            if (valid_b) atomicAdd(&counters[kCntValid], (unsigned long long)__popc(valid_b));
+            if (emit_b) slot0 = atomicAdd(&counters[kCntOut], (unsigned long long)__popc(emit_b));
         }
-        __syncthreads();
-        if (want_s[warp] & 1u) {
-            unsigned before = 0;
-            for (int q = 0; q < warp; q++) before += want_s[q] & 1u;
-            const unsigned long long slot = base_s + before;
-            if (slot < out_cap) {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(rec);
-                uint32_t* dst = reinterpret_cast<uint32_t*>(out + slot);
-                for (int q = lane; q < (int)(sizeof(ertgpu_candidate) / 4); q += 32) dst[q] = src[q];
+        slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+        const unsigned long long slot = slot0 + (unsigned long long)__popc(emit_b & ((1u << lane) - 1u));
+        if (emit && slot < out_cap) {
+            const unsigned long long s = (hw.gw << 5) + (unsigned long long)lane;
+            const long long block = first_block + (long long)(s >> shift);
+            uint32_t dg[11];   // 42 digits + 2 pad bytes
+#pragma unroll
+            for (int k = 0; k < 11; k++) dg[k] = 0;
+            if (has_dig) {
+                const uint16_t* d16 = reinterpret_cast<const uint16_t*>(r900_digits + (hw.slot + (unsigned long long)rank) * ERTGPU_R900_DIGITS);
+#pragma unroll
+                for (int k = 0; k < 21; k++) dg[k >> 1] |= (uint32_t)d16[k] << (16 * (k & 1));
             }
+            uint4* dst = reinterpret_cast<uint4*>(out + slot);
+            dst[0] = make_uint4((uint32_t)block, (uint32_t)((unsigned long long)block >> 32),
+                                (uint32_t)(s & (unsigned long long)(cfg.BS - 1)), (uint32_t)hw.preamble_id);
+            dst[1] = make_uint4(mask, has_dig ? ERTGPU_CAND_HAS_R900 : 0u, row[0], row[1]);
+#pragma unroll
+            for (int k = 0; k < 5; k++) dst[2 + k] = make_uint4(row[2 + 4 * k], row[3 + 4 * k], row[4 + 4 * k], row[5 + 4 * k]);
+            dst[7] = make_uint4(row[22], dg[0], dg[1], dg[2]);
+            dst[8] = make_uint4(dg[3], dg[4], dg[5], dg[6]);
+            dst[9] = make_uint4(dg[7], dg[8], dg[9], dg[10]);
         }
-        __syncthreads();
+        __syncwarp();   // the rows are rewritten by the next word
     }
 }
 
@@ -741,25 +761,6 @@ __global__ void r900_replay_kernel(const uint8_t* __restrict__ iq, const uint8_t
         uint8_t* d = digits + c * ERTGPU_R900_DIGITS;
         for (int k = 0; k < ERTGPU_R900_DIGITS; k++)
             d[k] = r900_digit(taps[4 * k], taps[4 * k + 1], taps[4 * k + 2], taps[4 * k + 3], taps[4 * k + 4]);
-    }
-}
-
-// Carry the last `hist_words` words of a call's plane to the front of the other plane, and the
-// last `hist_samples` IQ samples into the other history buffer (ping-pong: no overlap hazards).
-__global__ void carry_kernel(const uint32_t* __restrict__ plane_src, uint32_t* __restrict__ plane_dst,
-                             long long src_offset_words, int hist_words,
-                             const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_src,
-                             uint8_t* __restrict__ hist_dst, int hist_samples, long long nsamples) {
-    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int stride = gridDim.x * blockDim.x;
-    for (int i = i0; i < hist_words; i += stride) plane_dst[i] = plane_src[src_offset_words + i];
-    // hist_dst[k] (k in [0,hist_samples)) = sample (nsamples - hist_samples + k) relative to the call
-    for (int k = i0; k < hist_samples; k += stride) {
-        const long long j = nsamples - hist_samples + k;
-        uint16_t v;
-        if (j >= 0) v = reinterpret_cast<const uint16_t*>(iq)[j];
-        else v = reinterpret_cast<const uint16_t*>(hist_src)[hist_samples + j];
-        reinterpret_cast<uint16_t*>(hist_dst)[k] = v;
     }
 }
 

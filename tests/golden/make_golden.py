@@ -17,6 +17,31 @@ sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 
 here = os.path.dirname(os.path.abspath(__file__))
+
+# synthetic inputs shared with the Go-side generator (tests/golden/make_go_golden.sh, tests/test_go_golden.py):
+# name -> (msgtypes, chip length, samples, noise seed, packet seed, spacing)
+SYNTH_CASES = {
+    "synth_cl72_scm": ("scm", 72, 1 << 21, 0x5EED0101, 21, 1 << 18),
+    "synth_cl72_multi": ("scm,scm+,idm", 72, 1 << 22, 0x5EED0102, 22, 1 << 18),
+    "synth_cl72_r900": ("r900", 72, 1 << 21, 0x5EED0103, 23, 1 << 18),
+    "synth_cl32_all": ("scm,scm+,idm,r900", 32, 1 << 21, 0x5EED0104, 24, 1 << 17),
+}
+
+
+def synth_input(name):
+    from rtlamr_b200 import synth
+    mt, cl, n, seed, pseed, spacing = SYNTH_CASES[name]
+    pk, _ = synth.make_packets(mt, cl, n, seed=pseed, spacing=spacing)
+    return synth.host_fill(0, n, seed, pk)
+
+
+if len(sys.argv) == 3 and sys.argv[1] == "--synthetic-inputs":
+    for name in SYNTH_CASES:
+        synth_input(name).tofile(os.path.join(sys.argv[2], name + ".bin"))
+    sys.exit(0)
+if __name__ != "__main__":
+    raise ImportError("make_golden is a script; import SYNTH_CASES / synth_input via tests/test_go_golden.py's loader")
+
 src = "/root/reference/assets/sample.bin"
 dst = os.path.join(here, "sample_cl78.bin")
 if os.path.exists(src) and not os.path.exists(dst):

@@ -109,6 +109,17 @@ def test_synthetic_candidates_match_oracle(built, mt, cl, variant):
 def test_hybrid_magnitude_variant_is_bit_exact(built, monkeypatch, sample_iq):
     """demod_fast<72, 8, HYBRID>: Q magnitude computed with two float constants instead of the LUT."""
     monkeypatch.setenv("ERTGPU_FAST_WARPS", "108")
+    _variant_is_bit_exact(sample_iq)
+
+
+@pytest.mark.parametrize("knob", ["7", "8", "207", "208", "407", "408", "607", "608"])
+def test_demod_tuning_variants_are_bit_exact(built, monkeypatch, sample_iq, knob):
+    """Every (resident warps, staging depth, ring length) variant of the headline kernel gives the same bits."""
+    monkeypatch.setenv("ERTGPU_FAST_WARPS", knob)
+    _variant_is_bit_exact(sample_iq)
+
+
+def _variant_is_bit_exact(sample_iq):
     mt, cl = "scm", 72
     for src in ("synthetic", "sample", "extremes"):
         if src == "synthetic":
