@@ -83,7 +83,7 @@ struct ertgpu_handle {
     int demod_warps = 0;        // 0 default; tuning override (env ERTGPU_FAST_WARPS)
     bool search_legacy = false; // env ERTGPU_SEARCH_LEGACY: the per-bit-load Search kernel (kept for chip lengths like 78 and as a cross-check)
     int sm_count = 148;
-    bool r900_chain_shfl = false;  // env ERTGPU_R900_CHAIN=shfl: the shuffle form of the r900 chain's serial sum
+    int r900_chain_mode = 0;  // env ERTGPU_R900_CHAIN: (default) two-warp pipeline; "smem" = one warp, serial lane 0; "shfl" = one warp, shuffled sums
 
     // state of the last enqueued pipeline (for fetch and taps)
     bool pending = false;       // a pipeline is enqueued and not yet synchronised
@@ -357,14 +357,17 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
         r900_mark_kernel<<<148, 256, 0, st>>>(c, h->d_hits, h->cand_cap, h->d_counters, h->d_block_slot, h->d_slot_block,
                                               h->r900_slots, h->d_slot_count);
         CUDA_TRY(h, cudaGetLastError());
-        if (h->r900_chain_shfl) {
+        if (h->r900_chain_mode == 2) {
             r900_chain_kernel<true><<<148 * 16, kR900ChainWarps * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c,
                                                                        h->d_slot_block, h->r900_slots, h->d_slot_count,
                                                                        h->r900_span, h->d_r900_scratch);
-        } else {
+        } else if (h->r900_chain_mode == 1) {
             r900_chain_kernel<false><<<148 * 16, kR900ChainWarps * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c,
                                                                        h->d_slot_block, h->r900_slots, h->d_slot_count,
                                                                        h->r900_span, h->d_r900_scratch);
+        } else {   // default: producer / consumer warps per chain
+            r900_chain2_kernel<<<148 * 32, 64, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c, h->d_slot_block,
+                                                        h->r900_slots, h->d_slot_count, h->r900_span, h->d_r900_scratch);
         }
         CUDA_TRY(h, cudaGetLastError());
         r900_digits_kernel<<<148 * 4, 256, 0, st>>>(c, h->d_hits, h->cand_cap, h->d_counters, h->d_block_slot, h->r900_span,
@@ -754,7 +757,7 @@ static int allocate_impl(ertgpu_handle* h, int32_t device, int64_t max_blocks_pe
     h->demod_variant = demod_fast_variant(d.CL, d.BS);
     if (const char* e = getenv("ERTGPU_FAST_WARPS")) h->demod_warps = atoi(e);   // 100 * VAR + W, see launch_demod_fast
     if (const char* e = getenv("ERTGPU_SEARCH_LEGACY")) h->search_legacy = atoi(e) != 0;
-    if (const char* e = getenv("ERTGPU_R900_CHAIN")) h->r900_chain_shfl = strcmp(e, "shfl") == 0;
+    if (const char* e = getenv("ERTGPU_R900_CHAIN")) h->r900_chain_mode = strcmp(e, "shfl") == 0 ? 2 : (strcmp(e, "smem") == 0 ? 1 : 0);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
     if (h->sm_count < 1) h->sm_count = 148;
     h->cur_plane = h->cur_hist = 0;

@@ -705,6 +705,115 @@ r900_chain_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hi
     }
 }
 
+// ---- the same chain, software-pipelined over two warps ---------------------------------------
+//
+// A chain is span-1 (about 24 700) DEPENDENT float32 adds: its latency, not its work, is what the r900 path
+// pays (all chains of a call run concurrently).  One warp cannot both feed and run the serial section without
+// the feeding instructions sitting inside the dependent chain's issue stream (~10 cycles per add above).  Here a
+// CTA is two warps per chain: the PRODUCER warp fetches IQ bytes kR900Ahead groups ahead, looks the magnitudes
+// up and hands groups of 32 through a shared-memory ring; the CONSUMER warp's lane 0 does nothing but
+// LDS.128 -> 32 dependent FADD -> STS.128 per group (the next group's loads are issued before the adds); the
+// producer then streams the finished running sums to the scratch row.  mbarrier pairs (full / empty) per ring
+// slot carry the hand-offs.  Same additions in the same order as r900.go:96-100.
+constexpr int kChainRing = 8;    // groups in flight between the two warps
+constexpr int kChainAhead = 8;   // groups of raw IQ in flight in the producer's registers
+
+__global__ void __launch_bounds__(64)
+r900_chain2_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist, int hist_samples, int hist_valid,
+                   const float* __restrict__ lut_g, DevCfg cfg, const int* __restrict__ slot_block, int slot_cap,
+                   const unsigned int* __restrict__ slot_count, int span, float* __restrict__ scratch) {
+    __shared__ float lut[256];
+    __shared__ __align__(16) float m_s[kChainRing][32];
+    __shared__ __align__(16) float s_s[kChainRing][32];
+    __shared__ __align__(8) unsigned long long bars[2 * kChainRing];  // [0, R): full, [R, 2R): empty
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kChainRing]);
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < 2 * kChainRing; r++) mbar_init(full0 + 8 * r, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int nslots = *slot_count;
+    if (nslots > (unsigned)slot_cap) nslots = (unsigned)slot_cap;
+    const int ngroups = (span - 1 + 31) / 32;   // magnitudes 0 .. span-2 give csum[1 .. span-1]
+    uint32_t ph = 0;  // producer: parity to wait for on empty[r]; consumer: on full[r]  (bit r)
+    auto arrive = [](uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); };
+    for (unsigned int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+        const long long b = slot_block[slot];
+        const long long first = (b + 1) * cfg.BS - cfg.BUF;  // sample of the parser's signal[0]
+        float* out = scratch + (size_t)slot * (size_t)span;   // out[i] = csum[i], i in [0, span)
+        if (warp == 0) {
+            // ---- producer: magnitudes in, finished sums out
+            uint32_t rq[kChainAhead];
+#pragma unroll
+            for (int a = 0; a < kChainAhead; a++)
+                rq[a] = (a < ngroups) ? raw_at(iq, hist, hist_samples, hist_valid, first + a * 32 + lane) : 0x10000u;
+            auto flush = [&](int g) {   // group g's sums are complete in ring slot g % R
+                const int r = g % kChainRing;
+                mbar_wait(empty0 + 8 * r, (ph >> r) & 1u);
+                ph ^= 1u << r;
+                const int i = g * 32 + lane + 1;
+                if (i < span) out[i] = s_s[r][lane];
+                __syncwarp();   // every lane has read the slot before it is refilled
+            };
+            for (int g0 = 0; g0 < ngroups; g0 += kChainAhead) {
+#pragma unroll
+                for (int a = 0; a < kChainAhead; a++) {
+                    const int g = g0 + a;
+                    if (g >= ngroups) break;  // warp-uniform
+                    const int r = g % kChainRing;
+                    if (g >= kChainRing) flush(g - kChainRing);
+                    const float m = (g * 32 + lane < span - 1) ? mag_of(rq[a], lut) : 0.0f;
+                    rq[a] = (g + kChainAhead < ngroups)
+                                ? raw_at(iq, hist, hist_samples, hist_valid, first + (long long)(g + kChainAhead) * 32 + lane)
+                                : 0x10000u;
+                    m_s[r][lane] = m;
+                    __syncwarp();
+                    if (lane == 0) arrive(full0 + 8 * r);
+                }
+            }
+            for (int g = (ngroups > kChainRing ? ngroups - kChainRing : 0); g < ngroups; g++) flush(g);
+            if (lane == 0) out[0] = 0.0f;
+        } else if (lane == 0) {
+            // ---- consumer: the serial section and nothing else
+            float acc = 0.0f;
+            float4 v[8], vn[8];
+            mbar_wait(full0, ph & 1u);
+            ph ^= 1u;
+            {
+                const float4* mv = reinterpret_cast<const float4*>(&m_s[0][0]);
+#pragma unroll
+                for (int k = 0; k < 8; k++) vn[k] = mv[k];
+            }
+            for (int g = 0; g < ngroups; g++) {
+                const int r = g % kChainRing;
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = vn[k];
+                if (g + 1 < ngroups) {   // the next group's loads go out before this group's dependent adds
+                    const int rn = (g + 1) % kChainRing;
+                    mbar_wait(full0 + 8 * rn, (ph >> rn) & 1u);
+                    ph ^= 1u << rn;
+                    const float4* mv = reinterpret_cast<const float4*>(&m_s[rn][0]);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) vn[k] = mv[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {          // strictly left to right, r900.go:97-99
+                    acc = __fadd_rn(acc, v[k].x); v[k].x = acc;
+                    acc = __fadd_rn(acc, v[k].y); v[k].y = acc;
+                    acc = __fadd_rn(acc, v[k].z); v[k].z = acc;
+                    acc = __fadd_rn(acc, v[k].w); v[k].w = acc;
+                }
+                float4* sv = reinterpret_cast<float4*>(&s_s[r][0]);
+#pragma unroll
+                for (int k = 0; k < 8; k++) sv[k] = v[k];
+                arrive(empty0 + 8 * r);
+            }
+        }
+    }
+}
+
 __global__ void r900_digits_kernel(DevCfg cfg, const RawHit* __restrict__ hits, unsigned long long hit_cap,
                                    const unsigned long long* __restrict__ hit_count, const int* __restrict__ block_slot,
                                    int span, const float* __restrict__ scratch, uint8_t* __restrict__ digits) {

@@ -94,12 +94,12 @@ class Parsers:
         return _messages(out, n)
 
 
-def _parse_dedup(self, cands: np.ndarray, unique: bool = True, cap: int = 4096):
+def _parse_dedup(self, cands: np.ndarray, block_dedup: bool = True, cap: int = 4096):
     """parse() followed by the receive loop's cross-block dedup (main.go:244-260,292): (messages, duplicates dropped)."""
     cands = np.ascontiguousarray(cands)
     out = (_Msg * cap)()
     dup = C.c_longlong(0)
-    n = self._L.erthost_parse_dedup(self._h, cands.ctypes.data, len(cands), 1 if unique else 0, out, cap, C.byref(dup))
+    n = self._L.erthost_parse_dedup(self._h, cands.ctypes.data, len(cands), 1 if block_dedup else 0, out, cap, C.byref(dup))
     if n < 0:
         raise RuntimeError(self._L.erthost_error(self._h).decode())
     return _messages(out, min(n, cap)), int(dup.value)

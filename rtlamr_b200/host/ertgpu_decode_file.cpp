@@ -1,7 +1,7 @@
 // ertgpu_decode_file -- decode a raw uint8 IQ capture (rtl_sdr / rtlamr -samplefile format) or stdin
 // through the C++ mirror of rtlamr's receive loop (receiver.hpp) on the GPU and print one line per message
 // in rtlamr's plain format without the time fields (protocol/parse.go:119-121 StringNoOffset).
-//   ertgpu_decode_file [-msgtype=scm,idm|all] [-symbollength=72] [-unique=true] [-blocks=4096] [-device=0] FILE|- [FILE ...]
+//   ertgpu_decode_file [-msgtype=scm,idm|all] [-symbollength=72] [-blockdedup=true] [-blocks=4096] [-device=0] FILE|- [FILE ...]
 // Several files are a batch of independent streams through ONE decoder (buffers, tables and kernels set up once):
 // each starts from zeroed history with block numbers from 0, exactly as if it were decoded alone.
 #include <cstdio>
@@ -16,19 +16,19 @@ int main(int argc, char** argv) {
     std::vector<std::string> files;
     int chip = 72, device = 0;
     long long blocks = 4096;
-    bool unique = true, quiet = false;
+    bool block_dedup = true, quiet = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (a.rfind("-msgtype=", 0) == 0) msgtype = a.substr(9);
         else if (a.rfind("-symbollength=", 0) == 0) chip = atoi(a.c_str() + 14);
         else if (a.rfind("-device=", 0) == 0) device = atoi(a.c_str() + 8);
         else if (a.rfind("-blocks=", 0) == 0) blocks = atoll(a.c_str() + 8);
-        else if (a.rfind("-unique=", 0) == 0) unique = a.substr(8) != "false";
+        else if (a.rfind("-blockdedup=", 0) == 0) block_dedup = a.substr(12) != "false";
         else if (a == "-quiet") quiet = true;
         else files.push_back(a);
     }
     if (files.empty()) {
-        fprintf(stderr, "usage: %s [-msgtype=scm,scm+,idm,netidm,r900,r900bcd|all] [-symbollength=N] [-unique=true|false] "
+        fprintf(stderr, "usage: %s [-msgtype=scm,scm+,idm,netidm,r900,r900bcd|all] [-symbollength=N] [-blockdedup=true|false] "
                         "[-blocks=K] [-device=D] [-quiet] FILE|- [FILE ...]\n", argv[0]);
         return 2;
     }
@@ -43,7 +43,7 @@ int main(int argc, char** argv) {
                 return 1;
             }
             if (fi) rcvr.Reset();
-            auto st = rcvr.Run(in, unique, [&](const protocol::Message& m) {
+            auto st = rcvr.Run(in, block_dedup, [&](const protocol::Message& m) {
                 if (!quiet) printf("{Block:%lld Idx:%d %s:%s}\n", (long long)m.Block, m.Idx, m.MsgType().c_str(), m.String().c_str());
             });
             if (in != stdin) fclose(in);

@@ -2,6 +2,7 @@
 // (and a CLI) can drive Decoder/Parser exactly like rtlamr's main.go does (main.go:59-86,235).
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <sstream>
 
 #include "protocol.hpp"
@@ -29,9 +30,10 @@ struct erthost {
 // main.go:59-86: NewDecoder; for each -msgtype NewParser + RegisterProtocol; Allocate
 erthost* erthost_new(const char* msgtypes_csv, int chip_length, int device, long long max_blocks, long long max_cands,
                      char* errbuf, int errcap) {
+    std::unique_ptr<erthost> h;   // released only on success: a throwing NewParser / Allocate must not leak the handle
     try {
         protocol::RegisterStockParsers();
-        auto* h = new erthost();
+        h.reset(new erthost());
         std::stringstream ss(msgtypes_csv);
         std::string name;
         while (std::getline(ss, name, ',')) {
@@ -39,7 +41,7 @@ erthost* erthost_new(const char* msgtypes_csv, int chip_length, int device, long
             h->d.RegisterProtocol(protocol::NewParser(name, chip_length));
         }
         h->d.Allocate(device, max_blocks, max_cands);
-        return h;
+        return h.release();
     } catch (const std::exception& e) {
         if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", e.what());
         return nullptr;
@@ -48,16 +50,17 @@ erthost* erthost_new(const char* msgtypes_csv, int chip_length, int device, long
 
 // The same without Allocate: no device is touched, only erthost_parse works on such a handle.
 erthost* erthost_new_parse_only(const char* msgtypes_csv, int chip_length, char* errbuf, int errcap) {
+    std::unique_ptr<erthost> h;
     try {
         protocol::RegisterStockParsers();
-        auto* h = new erthost();
+        h.reset(new erthost());
         std::stringstream ss(msgtypes_csv);
         std::string name;
         while (std::getline(ss, name, ',')) {
             if (name.empty()) continue;
             h->d.RegisterProtocol(protocol::NewParser(name, chip_length));
         }
-        return h;
+        return h.release();
     } catch (const std::exception& e) {
         if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", e.what());
         return nullptr;
@@ -104,8 +107,8 @@ long long erthost_parse(erthost* h, const ertgpu_candidate* cands, long long n, 
 }
 
 // erthost_parse followed by the receive loop's cross-block dedup (main.go:244-260,292) with a fresh memory:
-// the messages rtlamr would print for this candidate list with -unique=`unique`.
-long long erthost_parse_dedup(erthost* h, const ertgpu_candidate* cands, long long n, int unique, erthost_msg* out,
+// the messages rtlamr would print for this candidate list with -blockdedup=`unique`.
+long long erthost_parse_dedup(erthost* h, const ertgpu_candidate* cands, long long n, int block_dedup, erthost_msg* out,
                               long long cap, long long* duplicates) {
     try {
         std::vector<protocol::MessagePtr> msgs, kept;
@@ -113,7 +116,7 @@ long long erthost_parse_dedup(erthost* h, const ertgpu_candidate* cands, long lo
         receiver::BlockDedup dd;
         receiver::Stats st;
         std::vector<const protocol::Message*> order;
-        dd.Filter(msgs, unique != 0, [&](const protocol::Message& m) { order.push_back(&m); }, st);
+        dd.Filter(msgs, block_dedup != 0, [&](const protocol::Message& m) { order.push_back(&m); }, st);
         if (duplicates) *duplicates = st.duplicates;
         // re-own in emit order (msgs keeps the objects alive until we return)
         std::vector<protocol::MessagePtr> view;

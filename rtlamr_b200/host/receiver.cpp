@@ -23,7 +23,13 @@ Receiver::Receiver(const std::string& msgtypes, int chipLength, int device, int6
     buf_bytes_ = (size_t)blocksPerCall * (size_t)d_.Cfg.BlockSize2;
     for (int k = 0; k < 2; k++) {
         void* p = nullptr;
-        if (ertgpu_host_alloc(&p, buf_bytes_) != ERTGPU_OK) throw std::runtime_error("pinned host allocation failed");
+        if (ertgpu_host_alloc(&p, buf_bytes_) != ERTGPU_OK) {
+            for (int j = 0; j < k; j++) {   // a constructor that throws runs no destructor: give back what it got
+                ertgpu_host_free(buf_[j]);
+                buf_[j] = nullptr;
+            }
+            throw std::runtime_error("pinned host allocation failed");
+        }
         buf_[k] = static_cast<uint8_t*>(p);
     }
 }
@@ -32,12 +38,12 @@ Receiver::~Receiver() {
     for (int k = 0; k < 2; k++) ertgpu_host_free(buf_[k]);
 }
 
-void Receiver::Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
+void Receiver::Filter(std::vector<protocol::MessagePtr>& msgs, bool block_dedup,
                       const std::function<void(const protocol::Message&)>& emit, Stats& st) {
-    dedup_.Filter(msgs, unique, emit, st);
+    dedup_.Filter(msgs, block_dedup, emit, st);
 }
 
-void BlockDedup::Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
+void BlockDedup::Filter(std::vector<protocol::MessagePtr>& msgs, bool block_dedup,
                         const std::function<void(const protocol::Message&)>& emit, Stats& st) {
     // main.go:221-224,244-260,292: `next` collects the digests of the current block, a message whose digest
     // was seen in the previous block is skipped, and the maps swap after every block -- including blocks
@@ -50,7 +56,7 @@ void BlockDedup::Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
         for (; i < msgs.size() && msgs[i]->Block == b; i++) {
             Digest dg = NewDigest(*msgs[i]);
             next.insert(dg);
-            if (unique && prev_.count(dg)) {
+            if (block_dedup && prev_.count(dg)) {
                 st.duplicates++;
                 continue;
             }
@@ -67,7 +73,7 @@ void Receiver::Reset() {
     dedup_.Reset();
 }
 
-Stats Receiver::Run(FILE* in, bool unique, const std::function<void(const protocol::Message&)>& emit) {
+Stats Receiver::Run(FILE* in, bool block_dedup, const std::function<void(const protocol::Message&)>& emit) {
     Stats st;
     const size_t bs2 = (size_t)d_.Cfg.BlockSize2;
     const auto t0 = std::chrono::steady_clock::now();
@@ -85,7 +91,7 @@ Stats Receiver::Run(FILE* in, bool unique, const std::function<void(const protoc
             auto msgs = d_.Decode(buf_[k], whole);
             st.blocks += (int64_t)(whole / bs2);
             st.bytes += (int64_t)whole;
-            Filter(msgs, unique, emit, st);
+            Filter(msgs, block_dedup, emit, st);
         }
         carry = have - whole;
         if (carry) memcpy(buf_[k ^ 1], buf_[k] + whole, carry);

@@ -33,7 +33,7 @@ struct Stats {
 class BlockDedup {
 public:
     // msgs grouped by ascending Block (what Decode returns); `emit` sees every message that is reported.
-    void Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
+    void Filter(std::vector<protocol::MessagePtr>& msgs, bool block_dedup,
                 const std::function<void(const protocol::Message&)>& emit, Stats& st);
     void Reset() {
         prev_.clear();
@@ -53,15 +53,15 @@ public:
 
     protocol::Decoder& decoder() { return d_; }
 
-    // Run over a FILE* until EOF.  `emit` is called once per reported message (after dedup when unique).
-    Stats Run(FILE* in, bool unique, const std::function<void(const protocol::Message&)>& emit);
+    // Run over a FILE* until EOF.  `emit` is called once per reported message (after the cross-block dedup when block_dedup).
+    Stats Run(FILE* in, bool block_dedup, const std::function<void(const protocol::Message&)>& emit);
 
     // Start a new, independent stream (the next file of a batch): zeroed Decoder history (decode.go:144-145),
     // block numbers restart at 0, empty dedup set.
     void Reset();
 
     // The dedup step on one Decode result (messages grouped by ascending Block), exposed for tests.
-    void Filter(std::vector<protocol::MessagePtr>& msgs, bool unique,
+    void Filter(std::vector<protocol::MessagePtr>& msgs, bool block_dedup,
                 const std::function<void(const protocol::Message&)>& emit, Stats& st);
 
 private:

@@ -162,7 +162,7 @@ def test_r900_chain_shuffle_form_agrees(built, monkeypatch, mt, cl):
     iq, _, _ = synth_stream(mt, cl, 1 << 21, spacing=1 << 18)
     o, cands, msgs = oracle_run(mt, cl, iq)
     out = {}
-    for form in ("shfl", "smem"):
+    for form in ("shfl", "smem", "pipe"):     # pipe = the default two-warp producer / consumer chain
         monkeypatch.setenv("ERTGPU_R900_CHAIN", form)
         h = capi.new_decoder(mt, cl)
         got = h.decode(whole_blocks(iq, h.cfg.block_size2))
@@ -170,7 +170,7 @@ def test_r900_chain_shuffle_form_agrees(built, monkeypatch, mt, cl):
         out[form] = np.sort(got, order=["block", "idx", "preamble_id"])
         h.close()
     assert (out["shfl"]["flags"] & capi.CAND_HAS_R900).any()
-    assert out["shfl"].tobytes() == out["smem"].tobytes()
+    assert out["shfl"].tobytes() == out["smem"].tobytes() == out["pipe"].tobytes()
     assert (out["shfl"]["check_mask"] != 0).any()
 
 
@@ -289,7 +289,7 @@ def test_device_resident_path_and_flags(built):
     assert np.array_equal(host["idx"], dev["idx"]) and np.array_equal(host["bytes"], dev["bytes"])
     ncand, nvalid = h.last_counts()
     assert ncand == len(host) and nvalid == int((host["check_mask"] != 0).sum()) and nvalid > 0
-    assert h.last_launches() >= 4
+    assert h.last_launches() >= 3          # demod, Search, Slice (+ history carry in the same kernel)
     h.reset()
     only = h.decode(iq, flags=capi.DECODE_ONLY_VALID)
     assert len(only) == nvalid and (only["check_mask"] != 0).all()

@@ -86,7 +86,7 @@ def test_r900_parser_alone_with_oracle_digits(built, mt, cl):
 
 def test_cross_block_dedup_rule_on_the_cpu(built):
     """main.go:244-260,292 (prev/next digest maps) in the C++ mirror, no device: parse the oracle's candidates of a
-    stream whose packets straddle block boundaries, with and without -unique, against the rule applied in Python to
+    stream whose packets straddle block boundaries, with and without the cross-block dedup, against the rule applied in Python to
     the oracle's messages."""
     from rtlamr_b200 import host, synth
     mt, cl = "scm", 72
@@ -114,8 +114,8 @@ def test_cross_block_dedup_rule_on_the_cpu(built):
         prev, prev_block = nxt, b
     p = host.Parsers(mt, cl)
     rec = _cand_records(cands)
-    uniq, dropped = p.parse_dedup(rec, unique=True)
-    alln, dropped_all = p.parse_dedup(rec, unique=False)
+    uniq, dropped = p.parse_dedup(rec, block_dedup=True)
+    alln, dropped_all = p.parse_dedup(rec, block_dedup=False)
     assert len(alln) == len(msgs) and dropped_all == 0
     assert len(uniq) == kept and dropped == len(msgs) - kept
     assert kept < len(msgs), "the stream should contain at least one packet that spans two blocks"
@@ -123,7 +123,7 @@ def test_cross_block_dedup_rule_on_the_cpu(built):
     # a gap in the block numbers empties the memory: the same candidates two blocks later are all reported again
     later = rec.copy()
     later["block"] += int(rec["block"].max()) + 3
-    twice, dropped2 = p.parse_dedup(np.concatenate([rec, later]), unique=True)
+    twice, dropped2 = p.parse_dedup(np.concatenate([rec, later]), block_dedup=True)
     assert len(twice) == 2 * kept and dropped2 == 2 * dropped
     p.close()
 

@@ -83,7 +83,7 @@ def test_cross_block_dedup_matches_main_go_rule(built, tmp_path):
                 kept += 1
         prev, prev_block = nxt, b
     uniq, _ = run_cli(str(path), f"-msgtype={mt}", f"-symbollength={cl}", "-blocks=64")
-    alln, _ = run_cli(str(path), f"-msgtype={mt}", f"-symbollength={cl}", "-blocks=64", "-unique=false")
+    alln, _ = run_cli(str(path), f"-msgtype={mt}", f"-symbollength={cl}", "-blocks=64", "-blockdedup=false")
     assert len(alln) == len(msgs)
     assert len(uniq) == kept
     assert kept < len(msgs), "the stream should contain at least one packet that spans two blocks"
