@@ -15,9 +15,22 @@
 // except r900 which reads its payload digits through Decoder.R900Digits (three-line patch in
 // INTEGRATION.md) because its DSP half also moved to the GPU.
 //
-// Written without a Go toolchain at hand (none in the build image): it is compiled and tested
-// only where Go exists.  The C++ mirror in rtlamr_b200/host/ exercises the same call sequence in
-// the parity tests.
+// STATUS: EXPERIMENTAL.  Written without a Go toolchain at hand (none in the build image): this file has
+// never been compiled; parity_test.go next to it is the first thing to run where Go and a B200 exist.
+// The C++ mirror in rtlamr_b200/host/ exercises the same call sequence in the parity tests.
+//
+// Two things a maintainer must know:
+//   * input memory: `input` is an ordinary Go slice (pageable).  ertgpu_decode stages pageable memory through
+//     pinned buffers owned by the handle (copy threads + chunked H2D), so the call is correct and reasonably
+//     fast for large calls (bench.py reports `e2e.pageable_input_value` next to the pinned figure), but one
+//     BlockSize2 (8-16 KiB) block per call, as main.go:166-186 reads them, pays a whole GPU pipeline and a
+//     synchronisation per block: feed K blocks per Decode (INTEGRATION.md 1, step 5) for throughput.
+//   * K > 1 and main.go's dedup: messages come back grouped per reference block and in block order, but the
+//     caller's `prev/next` digest maps (main.go:251-260) are swapped once per Decode CALL, so with K blocks per
+//     call a message repeated in the two blocks it straddles is suppressed inside the call only if the caller
+//     swaps the maps per block.  The channel carries no block index (protocol.Message has none): use K = 1 when
+//     main.go's exact dedup semantics matter, or take the C++ BlockDedup (rtlamr_b200/host/receiver.cpp), which
+//     swaps per block, as the model.
 package protocol
 
 /*

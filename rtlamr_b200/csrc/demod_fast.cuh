@@ -190,6 +190,7 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
         if (lut_base + kLutBytes + (uint32_t)nabove * G::kWarpBytes > sbase + dyn) __trap();
     }
 
+    pdl_launch_dependents();   // Search's CTAs may move in as this kernel's CTAs leave (they wait for the whole grid)
     // ---- prologue: LUT [v][lane] + zero column, barriers ----
     for (int v = warp; v < 256; v += WARPS) {   // row v: the value in the 32 lane columns, 0.0 in column 32
         const float x = lut_g[v];

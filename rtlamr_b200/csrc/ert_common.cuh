@@ -64,6 +64,13 @@ struct HitWord {
 // counters of one pipeline (unsigned long long each)
 enum { kCntHits = 0, kCntOut = 1, kCntValid = 2, kCntTile = 3, kCntWords = 4, kCntN = 8 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmaticStreamSerialization attribute may
+// become resident while the kernel in front of it on the stream is still running; pdl_wait() blocks until that
+// kernel has completed and its writes are visible (a no-op for an ordinary launch), pdl_launch_dependents() tells
+// the scheduler that the NEXT kernel's CTAs may be brought in as soon as there is room.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Plane bit order: stream bit g lives in word g>>5 at bit position 31-(g&31)
 // (MSB first, like the reference's packed bytes, decode.go:259-265).
 __device__ __forceinline__ uint32_t plane_bit(const uint32_t* __restrict__ plane, long long pos) {

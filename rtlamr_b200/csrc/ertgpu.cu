@@ -83,6 +83,7 @@ struct ertgpu_handle {
     int demod_warps = 0;        // 0 default; tuning override (env ERTGPU_FAST_WARPS)
     bool search_legacy = false; // env ERTGPU_SEARCH_LEGACY: the per-bit-load Search kernel (kept for chip lengths like 78 and as a cross-check)
     int sm_count = 148;
+    bool use_pdl = true;      // env ERTGPU_PDL=0: ordinary launches for Search and Slice
     int r900_chain_mode = 0;  // env ERTGPU_R900_CHAIN: (default) two-warp pipeline; "smem" = one warp, serial lane 0; "shfl" = one warp, shuffled sums
 
     // state of the last enqueued pipeline (for fetch and taps)
@@ -229,6 +230,23 @@ void fold_stage_times(ertgpu_handle* h) {
     h->stage_unread = 0;
 }
 
+// Launch `kern` as a programmatic dependent of the kernel in front of it on the stream (its CTAs may become resident
+// while that kernel drains; the kernel itself calls pdl_wait() before it reads anything).  pdl == false: ordinary launch.
+template <class K, class... Args>
+cudaError_t launch_dep(bool pdl, K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // Enqueue the whole per-call pipeline for `nblocks` blocks whose IQ bytes are at d_iq.
 int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uint32_t flags,
                      cudaStream_t st) {
@@ -248,6 +266,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
     }
 
     const bool tm = h->stage_timing;
+    const bool pdl = h->use_pdl && !tm;   // events recorded between the kernels would sit between primary and dependent
     if (tm) {
         if (h->stage_unread == ertgpu_handle::kStageSets) fold_stage_times(h);  // every earlier pipeline has been waited for
         h->ev_stage = h->ev_pool[h->stage_next];
@@ -296,7 +315,8 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
         static OncePerDevice once;                                                                               \
         if (once.first(h->device))                                                                               \
             CUDA_TRY(h, cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * kSlideMaxLoad + 4))); \
-        K<<<grid, kSlideThreads, smem, st>>>(plane, sl, h->d_hits, h->d_words, h->cand_cap, h->d_counters);      \
+        CUDA_TRY(h, launch_dep(pdl, K, dim3(grid), dim3(kSlideThreads), (size_t)smem, st, (const uint32_t*)plane, sl, h->d_hits, h->d_words, \
+                               h->cand_cap, h->d_counters));                                                     \
     } while (0)
 #define ERT_SLIDE(N, ...)                                                                    \
     do {                                                                                     \
@@ -316,9 +336,18 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
             } else if (c.npre == 2) {
                 ERT_SLIDE(2);
             } else if (c.npre == 3) {
-                ERT_SLIDE(3);
+                // scm, scm+, idm (or netidm) registered in that order: BASELINE.json configs[2]
+                if (slide_pattern(c, 0) == 0xF953u && slide_pattern(c, 1) == 0x16A3u && slide_pattern(c, 2) == 0x5555u)
+                    ERT_SLIDE(3, 0xF953u, 0x16A3u, 0x5555u);
+                else
+                    ERT_SLIDE(3);
             } else {
-                ERT_SLIDE(4);
+                // "-msgtype=all" = scm, scm+, idm, r900 (main.go:67-73)
+                if (c.npre == 4 && slide_pattern(c, 0) == 0xF953u && slide_pattern(c, 1) == 0x16A3u &&
+                    slide_pattern(c, 2) == 0x5555u && slide_pattern(c, 3) == 0x0000u)
+                    ERT_SLIDE(4, 0xF953u, 0x16A3u, 0x5555u, 0x0000u);
+                else
+                    ERT_SLIDE(4);
             }
 #undef ERT_SLIDE
 #undef ERT_SLIDE_K
@@ -328,7 +357,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
             unsigned grid = (unsigned)std::min<long long>(tiles, 148 * 4);
             if (grid < 1) grid = 1;
             const int mode = search_mode(c, p0);
-#define ERT_SEARCH(N, M) search_kernel<N, M><<<grid, kSearchThreads, smem, st>>>(plane, sp, h->d_hits, h->d_words, h->cand_cap, h->d_counters)
+#define ERT_SEARCH(N, M) CUDA_TRY(h, launch_dep(pdl, search_kernel<N, M>, dim3(grid), dim3(kSearchThreads), smem, st, (const uint32_t*)plane, sp, h->d_hits, h->d_words, h->cand_cap, h->d_counters))
 #define ERT_SEARCH_N(N) do { if (mode == 1) ERT_SEARCH(N, 1); else if (mode == 2) ERT_SEARCH(N, 2); else ERT_SEARCH(N, 0); } while (0)
             switch (c.npre) {
                 case 1: ERT_SEARCH_N(1); break;
@@ -342,7 +371,8 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
             const int nthr = 256;
             long long blocks = std::min<long long>((nwords + nthr - 1) / nthr, 148 * 16);
             if (blocks < 1) blocks = 1;
-            search_generic_kernel<<<(unsigned)blocks, nthr, 0, st>>>(plane, p0, nwords, c, h->d_hits, h->d_words, h->cand_cap, h->d_counters);
+            CUDA_TRY(h, launch_dep(pdl, search_generic_kernel, dim3((unsigned)blocks), dim3(nthr), 0, st, (const uint32_t*)plane, p0, nwords, c,
+                                   h->d_hits, h->d_words, h->cand_cap, h->d_counters));
         }
         CUDA_TRY(h, cudaGetLastError());
         h->launches++;
@@ -389,13 +419,15 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
         ca.iq = d_iq; ca.hist_src = hist; ca.hist_dst = hist_next; ca.hist_samples = c.hist_samples;
         ca.nsamples = nblocks * c.BS;
         const unsigned grid = (unsigned)h->sm_count * 4;
+        const bool dep = pdl && !h->has_r900;   // the r900 kernels between Search and Slice are ordinary launches
         if (c.PK <= 128)
-            extract_words_kernel<4><<<grid, kExtractWarps * 32, 0, st>>>(plane, p0, c, h->d_words, h->cand_cap, h->d_crc, h->gf, digits,
-                                                                    h->block_counter, flags, h->d_out, h->cand_cap, h->d_counters, ca);
+            CUDA_TRY(h, launch_dep(dep, extract_words_kernel<4>, dim3(grid), dim3(kExtractWarps * 32), 0, st, (const uint32_t*)plane, p0, c,
+                                   (const HitWord*)h->d_words, h->cand_cap, (const uint16_t*)h->d_crc, h->gf, digits, (long long)h->block_counter,
+                                   flags, h->d_out, h->cand_cap, h->d_counters, ca));
         else
-            extract_words_kernel<(ERTGPU_MAX_PACKET_BYTES * 8 + 31) / 32><<<grid, kExtractWarps * 32, 0, st>>>(
-                plane, p0, c, h->d_words, h->cand_cap, h->d_crc, h->gf, digits, h->block_counter, flags, h->d_out, h->cand_cap,
-                h->d_counters, ca);
+            CUDA_TRY(h, launch_dep(dep, extract_words_kernel<(ERTGPU_MAX_PACKET_BYTES * 8 + 31) / 32>, dim3(grid), dim3(kExtractWarps * 32), 0,
+                                   st, (const uint32_t*)plane, p0, c, (const HitWord*)h->d_words, h->cand_cap, (const uint16_t*)h->d_crc, h->gf,
+                                   digits, (long long)h->block_counter, flags, h->d_out, h->cand_cap, h->d_counters, ca));
         CUDA_TRY(h, cudaGetLastError());
         h->launches++;
     }
@@ -757,6 +789,7 @@ static int allocate_impl(ertgpu_handle* h, int32_t device, int64_t max_blocks_pe
     h->demod_variant = demod_fast_variant(d.CL, d.BS);
     if (const char* e = getenv("ERTGPU_FAST_WARPS")) h->demod_warps = atoi(e);   // 100 * VAR + W, see launch_demod_fast
     if (const char* e = getenv("ERTGPU_SEARCH_LEGACY")) h->search_legacy = atoi(e) != 0;
+    if (const char* e = getenv("ERTGPU_PDL")) h->use_pdl = atoi(e) != 0;
     if (const char* e = getenv("ERTGPU_R900_CHAIN")) h->r900_chain_mode = strcmp(e, "shfl") == 0 ? 2 : (strcmp(e, "smem") == 0 ? 1 : 0);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
     if (h->sm_count < 1) h->sm_count = 148;
@@ -871,7 +904,7 @@ int ertgpu_decode(ertgpu_handle* h, const uint8_t* iq, size_t nbytes, uint32_t f
         for (int k = 0; k < 2; k++) CUDA_TRY(h, cudaHostAlloc(&h->h_stage[k], h->stage_bytes, cudaHostAllocDefault));
         h->h_stage_bytes = h->stage_bytes;
     }
-    int copy_threads = 4;
+    int copy_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 4));  // ~6 GB/s per memcpy stream; 8 fill a PCIe 5 x16 link
     if (const char* e = getenv("ERTGPU_STAGE_THREADS")) copy_threads = std::min(64, std::max(1, atoi(e)));
     int64_t done = 0, launches = 0;
     for (int64_t i = 0; done < nblocks; i++) {

@@ -105,6 +105,8 @@ search_kernel(const uint32_t* __restrict__ plane, SearchParams sp, RawHit* __res
         mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_launch_dependents();
+    pdl_wait();
     __syncthreads();
     auto issue = [&](long long tile, int st) {
         mbar_arrive_expect_tx(bar0 + 8 * st, nload_bytes);
@@ -209,10 +211,12 @@ __device__ __noinline__ void slide_finish(const SlideParams* sp, int p, uint32_t
     emit_hit_word(m, gw, p, hits, words, hit_cap, hit_count);
 }
 
-// PAT: the first 16 preamble bits as a compile-time constant (bit 15 = preamble bit 0) for single-preamble
-// launches of the stock protocols: the compiler then folds two bits into each LOP3 (the probe is bound by
-// the half-rate integer pipe); kSlideRuntimePat = any preamble, bits taken from the launch constants.
-template <int NPRE, bool HALF, uint32_t PAT = kSlideRuntimePat>
+// PATp: the first 16 bits of preamble p as a compile-time constant (bit 15 = preamble bit 0) for launches of the
+// stock protocol sets (one preamble; scm,scm+,idm; scm,scm+,idm,r900 = "-msgtype=all"): the compiler then folds
+// two or three window words into each LOP3 (the probe is bound by the half-rate integer pipe);
+// kSlideRuntimePat = any preamble, bits taken from the launch constants.
+template <int NPRE, bool HALF, uint32_t PAT0 = kSlideRuntimePat, uint32_t PAT1 = kSlideRuntimePat,
+          uint32_t PAT2 = kSlideRuntimePat, uint32_t PAT3 = kSlideRuntimePat>
 __global__ void __launch_bounds__(kSlideThreads)
 search_slide_kernel(const uint32_t* __restrict__ plane, const __grid_constant__ SlideParams sp,
                     RawHit* __restrict__ hits, HitWord* __restrict__ words, unsigned long long hit_cap,
@@ -227,6 +231,8 @@ search_slide_kernel(const uint32_t* __restrict__ plane, const __grid_constant__ 
         mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_launch_dependents();
+    pdl_wait();   // the plane is complete (the demod kernel in front of this one has finished)
     __syncthreads();
     auto issue = [&](long long tile, int st) {
         mbar_arrive_expect_tx(bar0 + 8 * st, stage_bytes);
@@ -278,9 +284,11 @@ search_slide_kernel(const uint32_t* __restrict__ plane, const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < kSlideProbe; k += 2) {
                             const uint32_t e = E[(i + k / 2) % kSlideRing], o = O[(i + k / 2) % kSlideRing];
-                            if constexpr (PAT != kSlideRuntimePat) {
-                                me &= ((PAT >> (15 - k)) & 1u) ? e : ~e;
-                                mo &= ((PAT >> (14 - k)) & 1u) ? o : ~o;
+                            // p comes from a fully unrolled loop: the pattern and the branch below are compile-time
+                            const uint32_t pat = (p == 0) ? PAT0 : (p == 1) ? PAT1 : (p == 2) ? PAT2 : PAT3;
+                            if (pat != kSlideRuntimePat) {
+                                me &= ((pat >> (15 - k)) & 1u) ? e : ~e;
+                                mo &= ((pat >> (14 - k)) & 1u) ? o : ~o;
                             } else {
                                 me &= e ^ sp.inv[p][k];
                                 mo &= o ^ sp.inv[p][k + 1];
@@ -376,6 +384,8 @@ search_generic_kernel(const uint32_t* __restrict__ plane, long long p0, long lon
                       RawHit* __restrict__ hits, HitWord* __restrict__ words, unsigned long long hit_cap,
                       unsigned long long* __restrict__ hit_count) {
     const long long stride = (long long)gridDim.x * blockDim.x;
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride) {
         const long long base = p0 + (w << 5);
         for (int p = 0; p < cfg.npre; p++) {
@@ -459,6 +469,7 @@ extract_words_kernel(const uint32_t* __restrict__ plane, long long p0, const __g
     __shared__ uint16_t tab_s[ERTGPU_MAX_PROTOCOLS][256];
     __shared__ uint32_t rows_s[kExtractWarps][32 * kExtractRowWords];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();   // Search (and with it everything in front of it) has finished
     carry_part(carry, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     unsigned long long n = counters[kCntWords];
     if (n > word_cap) n = word_cap;
