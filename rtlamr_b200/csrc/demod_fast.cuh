@@ -35,6 +35,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <type_traits>
 
 #include "ert_common.cuh"
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
 demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __restrict__ iq,
                   const uint8_t* __restrict__ hist, int hist_samples, int hist_valid,
                   const float* __restrict__ lut_g, uint32_t* __restrict__ plane_out, long long nblocks, int BS,
-                  unsigned long long* __restrict__ tile_counter) {
+                  unsigned long long* __restrict__ tile_counter, long long dyn_tiles) {
     constexpr bool HYBRID = (VAR & 1) != 0;
     using G = FastGeom<CL, (VAR & 2) ? 3 : 2, (VAR & 4) != 0>;
     constexpr int L = G::L;
@@ -219,9 +220,25 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
     // Work tiles are claimed one ahead: the id of the NEXT tile is asked for when a tile starts and is known long
     // before the tile's last bodies, which refill the staging ring with the next tile's first bodies instead of
     // letting it drain -- a warp pays the TMA latency once, not once per tile.
+    //
+    // The first dyn_tiles tiles go out dynamically (atomic counter).  When the call does not fill the last round of
+    // SMs x WARPS tiles, the remaining tiles (at most 4 per SM) are pre-assigned instead: tile dyn_tiles + SM +
+    // SMs * w to warp w < 4 of each CTA, i.e. at most ONE per scheduler -- a warp that runs alone on its scheduler
+    // finishes a tile in ~0.6 of the shared time, while a dynamic hand-out lets two late tiles land on one scheduler
+    // next to an idle one.
+    bool static_used = false;
+    auto resolve = [&](unsigned long long claimed) -> unsigned long long {   // warp-uniform
+        if ((long long)claimed < dyn_tiles) return claimed;
+        if (!static_used && warp < 4) {
+            static_used = true;
+            const long long s = dyn_tiles + blockIdx.x + (long long)gridDim.x * warp;
+            if (s < ntiles) return (unsigned long long)s;
+        }
+        return ~0ull;
+    };
     unsigned long long tile = 0;
     if (lane == 0) tile = atomicAdd(tile_counter, 1ull);
-    tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+    tile = resolve(__shfl_sync(0xFFFFFFFFu, tile, 0));
     while ((long long)tile < ntiles) {
         unsigned long long next_raw = 0, next_tile = ~0ull;
         int npref_next = 0;
@@ -415,7 +432,7 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
                 if (s >= npref) issue(s, (st + s) % G::kStages);
             body(std::integral_constant<int, 0>{}, 0);
             body(std::integral_constant<int, 1>{}, 1);
-            next_tile = __shfl_sync(0xFFFFFFFFu, next_raw, 0);
+            next_tile = resolve(__shfl_sync(0xFFFFFFFFu, next_raw, 0));
 #pragma unroll 1
             for (int t = 2; t < nbody; t++) body(std::integral_constant<int, 2>{}, t);
         };
@@ -515,6 +532,26 @@ inline int fast_smem_bytes(int W, uint32_t sbase) {
     return (int)(lut_base + kLutBytes + (uint32_t)nabove * G::kWarpBytes - sbase);
 }
 
+// Tiles handed out dynamically; the rest (a last round that fills at most one warp per scheduler) is pre-assigned
+// inside the kernel.  ERTGPU_FAST_TAIL=0 keeps everything dynamic (tuning / cross-check).
+inline long long fast_dynamic_tiles(long long ntiles, long long grid, int W) {
+    static const bool enabled = [] { const char* e = getenv("ERTGPU_FAST_TAIL"); return !(e && atoi(e) == 0); }();
+    const long long cap = grid * W;
+    if (!enabled || W < 4 || cap <= 0) return ntiles;
+    const long long full = ntiles / cap, rest = ntiles - full * cap;
+    if (full < 1 || rest == 0 || rest > 4 * grid) return ntiles;
+    return full * cap;
+}
+// Rounds of SMs x W tiles a call takes, in units of an 8-warp round (measured on B200: a 7-warp round takes 0.94 of
+// an 8-warp one; a last round with at most one tile per scheduler ~0.62).
+inline double fast_round_cost(long long ntiles, long long sms, int W) {
+    const long long cap = sms * W, full = ntiles / cap, rest = ntiles - full * cap;
+    const double unit = W == 8 ? 1.0 : 0.94;
+    double last = 0.0;
+    if (rest > 0) last = (full >= 1 && rest <= 4 * sms) ? 0.62 : unit;
+    return full * unit + last;
+}
+
 template <int CL, int W, int VAR = 0>
 int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_samples, int hist_valid,
                          const float* lut, uint32_t* plane_out, long long nblocks, int BS,
@@ -558,7 +595,8 @@ int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_sample
     long long grid = (ntiles + W - 1) / W;
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, W * 32, smem, st>>>(map, iq, hist, hist_samples, hist_valid, lut, plane_out, nblocks, BS, tile_counter);
+    const long long dyn = fast_dynamic_tiles(ntiles, grid, W);
+    kern<<<(unsigned)grid, W * 32, smem, st>>>(map, iq, hist, hist_samples, hist_valid, lut, plane_out, nblocks, BS, tile_counter, dyn);
     return (int)cudaGetLastError();
 }
 
@@ -587,8 +625,7 @@ inline int launch_demod_fast(int variant, int warps, const uint8_t* iq, const ui
     if (warps == 0) {
         const int sms = sm_count_of(current_device());
         const long long T = (nblocks + 31) / 32;
-        const long long r8 = (T + sms * 8 - 1) / (sms * 8), r7 = (T + sms * 7 - 1) / (sms * 7);
-        seven = (double)r7 * 0.93 < (double)r8;
+        seven = fast_round_cost(T, sms, 7) < fast_round_cost(T, sms, 8);
     }
 #define ERT_FAST_CASE(N)                                                                         \
     case N:                                                                                      \

@@ -396,7 +396,7 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
                                                                        h->d_slot_block, h->r900_slots, h->d_slot_count,
                                                                        h->r900_span, h->d_r900_scratch);
         } else {   // default: producer / consumer warps per chain
-            r900_chain2_kernel<<<148 * 32, 64, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c, h->d_slot_block,
+            r900_chain2_kernel<<<(unsigned)h->sm_count * 16, 64, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c, h->d_slot_block,
                                                         h->r900_slots, h->d_slot_count, h->r900_span, h->d_r900_scratch);
         }
         CUDA_TRY(h, cudaGetLastError());

@@ -468,6 +468,7 @@ extract_words_kernel(const uint32_t* __restrict__ plane, long long p0, const __g
                      unsigned long long* __restrict__ counters, const __grid_constant__ CarryArgs carry) {
     __shared__ uint16_t tab_s[ERTGPU_MAX_PROTOCOLS][256];
     __shared__ uint32_t rows_s[kExtractWarps][32 * kExtractRowWords];
+    __shared__ uint32_t rs_s[21][32];   // r900: packed syndromes (5 x 5 bits) of symbol value v at message position pi
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_wait();   // Search (and with it everything in front of it) has finished
     carry_part(carry, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
@@ -475,6 +476,19 @@ extract_words_kernel(const uint32_t* __restrict__ plane, long long p0, const __g
     if (n > word_cap) n = word_cap;
     if ((unsigned long long)blockIdx.x * kExtractWarps >= n) return;
     for (int i = threadIdx.x; i < cfg.nproto * 256; i += blockDim.x) tab_s[i >> 8][i & 255] = crc_tables[i];
+    if (r900_digits != nullptr) {
+        for (int i = threadIdx.x; i < 21 * 32; i += blockDim.x) {
+            const int pi = i >> 5, v = i & 31;
+            const int q = pi < 16 ? pi : pi + 10;   // position in the 31-symbol word (r900.go:215-216)
+            uint32_t e5 = 0;
+            if (v != 0) {
+                const int lg = gf.log[v];
+#pragma unroll
+                for (int s2 = 0; s2 < 5; s2++) e5 |= (uint32_t)gf.exp[(lg + ((29 + s2) * (30 - q)) % 31) % 31] << (5 * s2);
+            }
+            rs_s[pi][v] = e5;
+        }
+    }
     __syncthreads();
     uint32_t* const row = &rows_s[warp][lane * kExtractRowWords];
     const uint8_t* const rowb = reinterpret_cast<const uint8_t*>(row);
@@ -530,40 +544,23 @@ extract_words_kernel(const uint32_t* __restrict__ plane, long long p0, const __g
                     }
                 }
             } else if (pr.check_kind == ERTGPU_CHECK_R900 && has_dig) {
-                // r900.go:199-221 across the warp, one candidate of the word at a time: lane q holds message symbol q of
-                // the 31-symbol RS word (16 data symbols, 10 zeros, 5 parity symbols; each symbol = two base-6 digits).
-                // The Horner evaluation of gf.go:163-169 at root a^(29+s) equals XOR_q msg[q] * root^(30-q).
-                uint32_t okbits = 0;
-                uint32_t m = hw.mask;
-                unsigned long long c = hw.slot;
-                while (m) {   // warp-uniform
-                    const int lead = __clz(m);
-                    m &= ~(0x80000000u >> lead);
-                    const uint8_t* dig = r900_digits + c * ERTGPU_R900_DIGITS;
-                    c++;
-                    int sym = 0;
+                // r900.go:199-221, one candidate per lane: 21 message symbols (two base-6 digits each) must be <= 31 and the
+                // five syndromes of the 31-symbol RS word (16 data symbols, 10 zeros, 5 parity symbols) must vanish.  The
+                // Horner evaluation of gf.go:163-169 at root a^(29+s) is linear over GF(32): S_s = XOR_q msg[q] * root_s^(30-q),
+                // so the five syndromes of symbol value v at position q are one packed table entry and a check is 21 lookups.
+                if (active) {
+                    const uint16_t* d16 = reinterpret_cast<const uint16_t*>(r900_digits + (hw.slot + (unsigned long long)rank) * ERTGPU_R900_DIGITS);
+                    uint32_t synd = 0;
                     bool bad = false;
-                    if (lane < 31 && (lane < 16 || lane >= 26)) {
-                        const int k = lane < 16 ? lane : lane - 10;
-                        sym = dig[2 * k] * 6 + dig[2 * k + 1];
-                        bad = sym > 31;
-                    }
-                    bool okc = __ballot_sync(0xFFFFFFFFu, bad) == 0;
-                    uint32_t synd = 0;  // 5 syndromes x 5 bits packed
-                    if (sym > 0 && sym < 32) {
-                        const int lg = gf.log[sym];
 #pragma unroll
-                        for (int s2 = 0; s2 < 5; s2++) {
-                            const int e = (lg + ((29 + s2) * (30 - lane)) % 31) % 31;
-                            synd |= (uint32_t)gf.exp[e] << (5 * s2);
-                        }
+                    for (int pi = 0; pi < 21; pi++) {
+                        const uint32_t dd = d16[pi];                       // digits 2*pi (low byte) and 2*pi+1
+                        const uint32_t sym = (dd & 0xFFu) * 6u + (dd >> 8);
+                        bad = bad || sym > 31u;
+                        synd ^= rs_s[pi][sym & 31u];
                     }
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) synd ^= __shfl_xor_sync(0xFFFFFFFFu, synd, d);
-                    okc = okc && synd == 0;
-                    if (okc) okbits |= 0x80000000u >> lead;
+                    ok = !bad && synd == 0;
                 }
-                ok = active && ((okbits >> (31 - lane)) & 1u);
             }
             if (ok) mask |= 1u << i;
         }
@@ -721,104 +718,148 @@ r900_chain_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hi
 // A chain is span-1 (about 24 700) DEPENDENT float32 adds: its latency, not its work, is what the r900 path
 // pays (all chains of a call run concurrently).  One warp cannot both feed and run the serial section without
 // the feeding instructions sitting inside the dependent chain's issue stream (~10 cycles per add above).  Here a
-// CTA is two warps per chain: the PRODUCER warp fetches IQ bytes kR900Ahead groups ahead, looks the magnitudes
-// up and hands groups of 32 through a shared-memory ring; the CONSUMER warp's lane 0 does nothing but
-// LDS.128 -> 32 dependent FADD -> STS.128 per group (the next group's loads are issued before the adds); the
-// producer then streams the finished running sums to the scratch row.  mbarrier pairs (full / empty) per ring
-// slot carry the hand-offs.  Same additions in the same order as r900.go:96-100.
-constexpr int kChainRing = 8;    // groups in flight between the two warps
-constexpr int kChainAhead = 8;   // groups of raw IQ in flight in the producer's registers
+// CTA is two warps and kChainsPerCta chains:
+//  * the PRODUCER warp fetches IQ bytes kChainAhead units ahead, looks the magnitudes up and hands units of
+//    kChainUnit samples per chain through a shared-memory ring; afterwards it streams the finished running sums
+//    of a unit to the chains' scratch rows;
+//  * the CONSUMER warp runs one chain on each of its lanes 0, 8, 16, 24 (SIMT: one FADD instruction advances all
+//    of them, so four chains cost the issue slots and registers of one) and does nothing but LDS.128 -> 32 dependent
+//    FADD -> STS.128 per 32 samples; the next 32 magnitudes are loaded before the adds, and the next unit's
+//    barrier is PROBED (mbarrier.test_wait) at the start of the current unit, so neither the shared-memory latency
+//    nor the barrier's sits in the dependent chain.
+// mbarrier pairs (full / empty) per ring slot carry the hand-offs, one pair of operations per kChainUnit samples.
+// Same additions in the same order as r900.go:96-100.  Four chains per CTA keep every chain of a 4 GiB call
+// resident at once (the kernel's time is ONE chain's latency as long as that holds).
+constexpr int kChainsPerCta = 4;
+constexpr int kChainUnit = 128;   // samples per hand-off
+constexpr int kChainRing = 4;     // units in flight between the two warps
+constexpr int kChainAhead = 2;    // units of raw IQ in flight in the producer's registers
+constexpr int kChainPitch = kChainUnit + 4;  // floats per chain row of a ring slot: the 4 consumer lanes hit 4 different bank groups
 
 __global__ void __launch_bounds__(64)
 r900_chain2_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist, int hist_samples, int hist_valid,
                    const float* __restrict__ lut_g, DevCfg cfg, const int* __restrict__ slot_block, int slot_cap,
                    const unsigned int* __restrict__ slot_count, int span, float* __restrict__ scratch) {
     __shared__ float lut[256];
-    __shared__ __align__(16) float m_s[kChainRing][32];
-    __shared__ __align__(16) float s_s[kChainRing][32];
+    __shared__ __align__(16) float m_s[kChainRing][kChainsPerCta][kChainPitch];
+    __shared__ __align__(16) float s_s[kChainRing][kChainsPerCta][kChainPitch];
     __shared__ __align__(8) unsigned long long bars[2 * kChainRing];  // [0, R): full, [R, 2R): empty
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kChainRing]);
     if (threadIdx.x == 0) {
-        for (int r = 0; r < 2 * kChainRing; r++) mbar_init(full0 + 8 * r, 1);
+        for (int r = 0; r < kChainRing; r++) {
+            mbar_init(full0 + 8 * r, 1);                 // the producer's lane 0
+            mbar_init(empty0 + 8 * r, kChainsPerCta);    // the consumer lanes
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned int nslots = *slot_count;
     if (nslots > (unsigned)slot_cap) nslots = (unsigned)slot_cap;
-    const int ngroups = (span - 1 + 31) / 32;   // magnitudes 0 .. span-2 give csum[1 .. span-1]
+    const int nunits = (span - 1 + kChainUnit - 1) / kChainUnit;   // magnitudes 0 .. span-2 give csum[1 .. span-1]
     uint32_t ph = 0;  // producer: parity to wait for on empty[r]; consumer: on full[r]  (bit r)
     auto arrive = [](uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); };
-    for (unsigned int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
-        const long long b = slot_block[slot];
-        const long long first = (b + 1) * cfg.BS - cfg.BUF;  // sample of the parser's signal[0]
-        float* out = scratch + (size_t)slot * (size_t)span;   // out[i] = csum[i], i in [0, span)
+    for (unsigned int slot0 = blockIdx.x * kChainsPerCta; slot0 < nslots; slot0 += gridDim.x * kChainsPerCta) {
         if (warp == 0) {
             // ---- producer: magnitudes in, finished sums out
-            uint32_t rq[kChainAhead];
+            long long first[kChainsPerCta];
+            float* out[kChainsPerCta];
+            bool valid[kChainsPerCta];
+#pragma unroll
+            for (int ch = 0; ch < kChainsPerCta; ch++) {
+                valid[ch] = slot0 + ch < nslots;
+                const long long b = valid[ch] ? slot_block[slot0 + ch] : 0;
+                first[ch] = (b + 1) * cfg.BS - cfg.BUF;                            // sample of the parser's signal[0]
+                out[ch] = scratch + (size_t)(slot0 + ch) * (size_t)span;           // out[i] = csum[i], i in [0, span)
+            }
+            uint32_t rq[kChainAhead][kChainsPerCta][kChainUnit / 32];
+            auto fetch = [&](int u, int ch, int j) -> uint32_t {
+                const int i = u * kChainUnit + j * 32 + lane;
+                return (valid[ch] && u < nunits && i < span - 1) ? raw_at(iq, hist, hist_samples, hist_valid, first[ch] + i) : 0x10000u;
+            };
 #pragma unroll
             for (int a = 0; a < kChainAhead; a++)
-                rq[a] = (a < ngroups) ? raw_at(iq, hist, hist_samples, hist_valid, first + a * 32 + lane) : 0x10000u;
-            auto flush = [&](int g) {   // group g's sums are complete in ring slot g % R
-                const int r = g % kChainRing;
+#pragma unroll
+                for (int ch = 0; ch < kChainsPerCta; ch++)
+#pragma unroll
+                    for (int j = 0; j < kChainUnit / 32; j++) rq[a][ch][j] = fetch(a, ch, j);
+            auto flush = [&](int u) {   // unit u's sums are complete in ring slot u % R
+                const int r = u % kChainRing;
                 mbar_wait(empty0 + 8 * r, (ph >> r) & 1u);
                 ph ^= 1u << r;
-                const int i = g * 32 + lane + 1;
-                if (i < span) out[i] = s_s[r][lane];
+#pragma unroll
+                for (int ch = 0; ch < kChainsPerCta; ch++)
+#pragma unroll
+                    for (int j = 0; j < kChainUnit / 32; j++) {
+                        const int i = u * kChainUnit + j * 32 + lane + 1;
+                        if (valid[ch] && i < span) out[ch][i] = s_s[r][ch][j * 32 + lane];
+                    }
                 __syncwarp();   // every lane has read the slot before it is refilled
             };
-            for (int g0 = 0; g0 < ngroups; g0 += kChainAhead) {
+            for (int u0 = 0; u0 < nunits; u0 += kChainAhead) {
 #pragma unroll
                 for (int a = 0; a < kChainAhead; a++) {
-                    const int g = g0 + a;
-                    if (g >= ngroups) break;  // warp-uniform
-                    const int r = g % kChainRing;
-                    if (g >= kChainRing) flush(g - kChainRing);
-                    const float m = (g * 32 + lane < span - 1) ? mag_of(rq[a], lut) : 0.0f;
-                    rq[a] = (g + kChainAhead < ngroups)
-                                ? raw_at(iq, hist, hist_samples, hist_valid, first + (long long)(g + kChainAhead) * 32 + lane)
-                                : 0x10000u;
-                    m_s[r][lane] = m;
+                    const int u = u0 + a;
+                    if (u >= nunits) break;  // warp-uniform
+                    const int r = u % kChainRing;
+                    if (u >= kChainRing) flush(u - kChainRing);
+#pragma unroll
+                    for (int ch = 0; ch < kChainsPerCta; ch++)
+#pragma unroll
+                        for (int j = 0; j < kChainUnit / 32; j++) {
+                            m_s[r][ch][j * 32 + lane] = mag_of(rq[a][ch][j], lut);   // 0.0 past the end of the chain
+                            rq[a][ch][j] = fetch(u + kChainAhead, ch, j);
+                        }
                     __syncwarp();
                     if (lane == 0) arrive(full0 + 8 * r);
                 }
             }
-            for (int g = (ngroups > kChainRing ? ngroups - kChainRing : 0); g < ngroups; g++) flush(g);
-            if (lane == 0) out[0] = 0.0f;
-        } else if (lane == 0) {
-            // ---- consumer: the serial section and nothing else
+            for (int u = (nunits > kChainRing ? nunits - kChainRing : 0); u < nunits; u++) flush(u);
+            if (lane < kChainsPerCta && slot0 + lane < nslots) scratch[(size_t)(slot0 + lane) * (size_t)span] = 0.0f;   // csum[0]
+        } else if ((lane & 7) == 0) {
+            // ---- consumer: four serial sections side by side, and nothing else
+            const int ch = lane >> 3;
             float acc = 0.0f;
             float4 v[8], vn[8];
             mbar_wait(full0, ph & 1u);
             ph ^= 1u;
             {
-                const float4* mv = reinterpret_cast<const float4*>(&m_s[0][0]);
+                const float4* mv = reinterpret_cast<const float4*>(&m_s[0][ch][0]);
 #pragma unroll
                 for (int k = 0; k < 8; k++) vn[k] = mv[k];
             }
-            for (int g = 0; g < ngroups; g++) {
-                const int r = g % kChainRing;
+            for (int u = 0; u < nunits; u++) {
+                const int r = u % kChainRing, rn = (u + 1) % kChainRing;
+                const bool have_next = u + 1 < nunits;
+                // probe the next unit's barrier now: the answer is needed three sub-groups (~400 cycles) from here
+                bool ready = have_next ? mbar_test(full0 + 8 * rn, (ph >> rn) & 1u) : false;
 #pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = vn[k];
-                if (g + 1 < ngroups) {   // the next group's loads go out before this group's dependent adds
-                    const int rn = (g + 1) % kChainRing;
-                    mbar_wait(full0 + 8 * rn, (ph >> rn) & 1u);
-                    ph ^= 1u << rn;
-                    const float4* mv = reinterpret_cast<const float4*>(&m_s[rn][0]);
+                for (int g = 0; g < kChainUnit / 32; g++) {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) vn[k] = mv[k];
+                    for (int k = 0; k < 8; k++) v[k] = vn[k];
+                    if (g + 1 < kChainUnit / 32) {   // the next 32 magnitudes go out before this group's dependent adds
+                        const float4* mv = reinterpret_cast<const float4*>(&m_s[r][ch][(g + 1) * 32]);
+#pragma unroll
+                        for (int k = 0; k < 8; k++) vn[k] = mv[k];
+                    } else if (have_next) {
+                        if (!ready) mbar_wait(full0 + 8 * rn, (ph >> rn) & 1u);
+                        ph ^= 1u << rn;
+                        const float4* mv = reinterpret_cast<const float4*>(&m_s[rn][ch][0]);
+#pragma unroll
+                        for (int k = 0; k < 8; k++) vn[k] = mv[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {          // strictly left to right, r900.go:97-99
+                        acc = __fadd_rn(acc, v[k].x); v[k].x = acc;
+                        acc = __fadd_rn(acc, v[k].y); v[k].y = acc;
+                        acc = __fadd_rn(acc, v[k].z); v[k].z = acc;
+                        acc = __fadd_rn(acc, v[k].w); v[k].w = acc;
+                    }
+                    float4* sv = reinterpret_cast<float4*>(&s_s[r][ch][g * 32]);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) sv[k] = v[k];
                 }
-#pragma unroll
-                for (int k = 0; k < 8; k++) {          // strictly left to right, r900.go:97-99
-                    acc = __fadd_rn(acc, v[k].x); v[k].x = acc;
-                    acc = __fadd_rn(acc, v[k].y); v[k].y = acc;
-                    acc = __fadd_rn(acc, v[k].z); v[k].z = acc;
-                    acc = __fadd_rn(acc, v[k].w); v[k].w = acc;
-                }
-                float4* sv = reinterpret_cast<float4*>(&s_s[r][0]);
-#pragma unroll
-                for (int k = 0; k < 8; k++) sv[k] = v[k];
                 arrive(empty0 + 8 * r);
             }
         }
@@ -833,8 +874,10 @@ __global__ void r900_digits_kernel(DevCfg cfg, const RawHit* __restrict__ hits, 
     const unsigned long long total = n * ERTGPU_R900_DIGITS;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const unsigned long long c = t / ERTGPU_R900_DIGITS;
-        const int k = (int)(t % ERTGPU_R900_DIGITS);
+        // lanes run across HITS (neighbouring hits are neighbouring sample phases of one packet: their five running
+        // sums are neighbouring floats of the scratch row), digit positions across the outer index
+        const unsigned long long c = t % n;
+        const int k = (int)(t / n);
         const RawHit h = hits[c];
         if (!cfg.pre_has_r900[h.preamble_id]) continue;
         const long long b = (long long)(h.s >> bs_shift(cfg));

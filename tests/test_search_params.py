@@ -26,9 +26,13 @@ def build(tmp_path_factory, name):
 
 
 @pytest.fixture(scope="module")
-def demod_geom(tmp_path_factory):
-    exe = build(tmp_path_factory, "demod_geom")
-    return json.loads(subprocess.run([exe], check=True, capture_output=True, text=True).stdout)
+def demod_geom_exe(tmp_path_factory):
+    return build(tmp_path_factory, "demod_geom")
+
+
+@pytest.fixture(scope="module")
+def demod_geom(demod_geom_exe):
+    return json.loads(subprocess.run([demod_geom_exe], check=True, capture_output=True, text=True).stdout)
 
 
 @pytest.fixture(scope="module")
@@ -113,3 +117,21 @@ def test_demod_fast_geometry(demod_geom):
         assert r["smem7"] <= r["smem"] <= r["smem3"]
     by = {r["CL"]: r for r in demod_geom}
     assert by[72]["L"] == 88 and by[72]["pad"] == 32 and by[72]["smem"] == 65536 + 65536 + 3 * 2 * 32 * 176 - 1024
+
+
+def test_demod_tile_plan_covers_every_tile_once(demod_geom_exe):
+    """The last round of work tiles: when it would fill at most one warp per scheduler it is pre-assigned (tile
+    dyn + SM + SMs * w to warp w < 4), otherwise everything stays dynamic.  Every tile is owned exactly once."""
+    exe = demod_geom_exe
+    for ntiles, sms, W in ((4096, 148, 8), (4096, 148, 7), (32768, 148, 8), (1184 * 3 + 592, 148, 8), (1184 * 3 + 593, 148, 8),
+                           (1184 * 5, 148, 8), (100, 148, 8), (1, 148, 8), (1184 + 1, 148, 8), (16384, 132, 8)):
+        r = json.loads(subprocess.run([exe, "plan", str(ntiles), str(sms), str(W)], check=True, capture_output=True, text=True).stdout)
+        assert not r["dup"] and r["dyn"] + r["static_covered"] == ntiles, r
+        cap = r["grid"] * W
+        rest = ntiles % cap if ntiles >= cap else 0
+        if ntiles >= cap and 0 < rest <= 4 * r["grid"]:
+            assert r["dyn"] == ntiles - rest and r["per_sched_max"] == 1
+        else:
+            assert r["dyn"] == ntiles
+    r = json.loads(subprocess.run([exe, "plan", "4096", "148", "8"], check=True, capture_output=True, text=True).stdout)
+    assert r["dyn"] == 3552 and r["cost8"] < r["cost7"]      # 1 GiB scm: 3 dynamic rounds of 8 warps + 544 pre-assigned tiles
