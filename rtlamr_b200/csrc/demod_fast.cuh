@@ -226,6 +226,7 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
     // SMs * w to warp w < 4 of each CTA, i.e. at most ONE per scheduler -- a warp that runs alone on its scheduler
     // finishes a tile in ~0.6 of the shared time, while a dynamic hand-out lets two late tiles land on one scheduler
     // next to an idle one.
+    constexpr unsigned long long kNoTile = 0x7FFFFFFFFFFFFFFFull;   // compares above every tile as a signed value too
     bool static_used = false;
     auto resolve = [&](unsigned long long claimed) -> unsigned long long {   // warp-uniform
         if ((long long)claimed < dyn_tiles) return claimed;
@@ -234,13 +235,13 @@ demod_fast_kernel(const __grid_constant__ CUtensorMap iq_map, const uint8_t* __r
             const long long s = dyn_tiles + blockIdx.x + (long long)gridDim.x * warp;
             if (s < ntiles) return (unsigned long long)s;
         }
-        return ~0ull;
+        return kNoTile;
     };
     unsigned long long tile = 0;
     if (lane == 0) tile = atomicAdd(tile_counter, 1ull);
     tile = resolve(__shfl_sync(0xFFFFFFFFu, tile, 0));
     while ((long long)tile < ntiles) {
-        unsigned long long next_raw = 0, next_tile = ~0ull;
+        unsigned long long next_raw = 0, next_tile = kNoTile;
         int npref_next = 0;
         if (lane == 0) next_raw = atomicAdd(tile_counter, 1ull);  // consumed after the lead-in bodies
 
