@@ -112,10 +112,18 @@ def test_hybrid_magnitude_variant_is_bit_exact(built, monkeypatch, sample_iq):
     _variant_is_bit_exact(sample_iq)
 
 
-@pytest.mark.parametrize("knob", ["7", "8", "207", "208", "407", "408", "607", "608"])
+@pytest.mark.parametrize("knob", ["7", "8", "208", "408", "812", "2412", "2410", "4014", "6408", "7212"])
 def test_demod_tuning_variants_are_bit_exact(built, monkeypatch, sample_iq, knob):
-    """Every (resident warps, staging depth, ring length) variant of the headline kernel gives the same bits."""
+    """Every variant of the headline kernel gives the same bits: resident warps, staging depth, ring length, and the
+    rings in Tensor Memory (8xx: chip-sum ring; 24xx: + half of the Q magnitudes computed; 40xx: + part of the
+    running-sum ring; 64xx/72xx: scalar instead of packed adds)."""
     monkeypatch.setenv("ERTGPU_FAST_WARPS", knob)
+    _variant_is_bit_exact(sample_iq)
+
+
+def test_register_ring_default_is_bit_exact(built, monkeypatch, sample_iq):
+    """ERTGPU_FAST_TMEM=0: the round-1 kernel (both rings in registers, 7 or 8 warps) stays selectable and exact."""
+    monkeypatch.setenv("ERTGPU_FAST_TMEM", "0")
     _variant_is_bit_exact(sample_iq)
 
 
