@@ -387,25 +387,28 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
         r900_mark_kernel<<<148, 256, 0, st>>>(c, h->d_hits, h->cand_cap, h->d_counters, h->d_block_slot, h->d_slot_block,
                                               h->r900_slots, h->d_slot_count);
         CUDA_TRY(h, cudaGetLastError());
+        // the two-warp pipeline loads 8 samples (16 bytes) at a time: chain starts and the call's bytes must be 16-byte aligned
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(d_iq) & 15u) == 0 && (reinterpret_cast<uintptr_t>(hist) & 15u) == 0 &&
+                            c.BUF % 8 == 0 && c.BS % 8 == 0 && c.hist_samples % 8 == 0;
         if (h->r900_chain_mode == 2) {
             r900_chain_kernel<true><<<148 * 16, kR900ChainWarps * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c,
                                                                        h->d_slot_block, h->r900_slots, h->d_slot_count,
                                                                        h->r900_span, h->d_r900_scratch);
-        } else if (h->r900_chain_mode == 1) {
+        } else if (h->r900_chain_mode == 1 || !vec_ok) {
             r900_chain_kernel<false><<<148 * 16, kR900ChainWarps * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c,
                                                                        h->d_slot_block, h->r900_slots, h->d_slot_count,
                                                                        h->r900_span, h->d_r900_scratch);
         } else {   // default: producer / consumer warps per chain
-            r900_chain2_kernel<<<(unsigned)h->sm_count * 16, 64, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c, h->d_slot_block,
+            r900_chain2_kernel<<<(unsigned)h->sm_count * 2, (kChainProducers + 1) * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, c, h->d_slot_block,
                                                         h->r900_slots, h->d_slot_count, h->r900_span, h->d_r900_scratch);
         }
         CUDA_TRY(h, cudaGetLastError());
-        r900_digits_kernel<<<148 * 4, 256, 0, st>>>(c, h->d_hits, h->cand_cap, h->d_counters, h->d_block_slot, h->r900_span,
+        r900_digits_kernel<<<148 * 16, 256, 0, st>>>(c, h->d_hits, h->cand_cap, h->d_counters, h->d_block_slot, h->r900_span,
                                                     h->d_r900_scratch, h->d_digits);
         CUDA_TRY(h, cudaGetLastError());
         // blocks that found no scratch slot: exact per-candidate replay
         r900_replay_kernel<<<148, 64, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c, h->d_hits,
-                                               h->cand_cap, h->d_counters, h->d_block_slot, h->d_digits);
+                                               h->cand_cap, h->d_counters, h->d_block_slot, h->d_digits, h->d_slot_count, h->r900_slots);
         CUDA_TRY(h, cudaGetLastError());
         h->launches += 4;
         digits = h->d_digits;
@@ -779,7 +782,7 @@ static int allocate_impl(ertgpu_handle* h, int32_t device, int64_t max_blocks_pe
         CUDA_TRY(h, cudaMalloc(&h->d_block_slot, (size_t)max_blocks_per_call * sizeof(int)));
         CUDA_TRY(h, cudaMalloc(&h->d_slot_block, (size_t)h->r900_slots * sizeof(int)));
         CUDA_TRY(h, cudaMalloc(&h->d_slot_count, sizeof(unsigned int)));
-        CUDA_TRY(h, cudaMalloc(&h->d_r900_scratch, (size_t)h->r900_slots * (size_t)h->r900_span * sizeof(float)));
+        CUDA_TRY(h, cudaMalloc(&h->d_r900_scratch, (size_t)h->r900_slots * r900_pitch(h->r900_span) * sizeof(float) + 64));
     }
     CUDA_TRY(h, cudaMalloc(&h->d_counters, kCntN * sizeof(unsigned long long)));
     CUDA_TRY(h, cudaHostAlloc(&h->h_counters, kCntN * sizeof(unsigned long long), cudaHostAllocDefault));

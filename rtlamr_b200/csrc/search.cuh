@@ -611,6 +611,12 @@ extract_words_kernel(const uint32_t* __restrict__ plane, long long p0, const __g
 // them in the reference's order -- (3) one thread per (hit, digit) evaluates the three 4-chip
 // correlators.  Blocks beyond the scratch capacity fall back to r900_replay_kernel.
 
+// Scratch row of a slot: csum[i] sits at row[i] with row = base + slot * pitch + 3, so that csum[1], csum[5], ... are 16-byte
+// aligned (the chain kernel stores four running sums per instruction; csum[0] = 0 is never produced by an add).
+__host__ __device__ __forceinline__ size_t r900_pitch(int span) { return (size_t)((span + 255) / 256) * 256 + 8; }   // whole hand-off units + the 3-float offset: the chain kernel stores whole vectors
+__device__ __forceinline__ float* r900_row(float* scratch, long long slot, int span) { return scratch + (size_t)slot * r900_pitch(span) + 3; }
+__device__ __forceinline__ const float* r900_row(const float* scratch, long long slot, int span) { return scratch + (size_t)slot * r900_pitch(span) + 3; }
+
 __global__ void r900_mark_kernel(DevCfg cfg, const RawHit* __restrict__ hits, unsigned long long hit_cap,
                                  const unsigned long long* __restrict__ hit_count, int* __restrict__ block_slot,
                                  int* __restrict__ slot_block, int slot_cap, unsigned int* __restrict__ slot_count) {
@@ -654,7 +660,7 @@ r900_chain_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hi
     for (unsigned int slot = blockIdx.x * kR900ChainWarps + warp; slot < nslots; slot += gridDim.x * kR900ChainWarps) {
         const long long b = slot_block[slot];
         const long long first = (b + 1) * cfg.BS - cfg.BUF;  // sample of the parser's signal[0]
-        float* out = scratch + (size_t)slot * (size_t)span;   // out[i] = csum[i], i in [0, span)
+        float* out = r900_row(scratch, slot, span);   // out[i] = csum[i], i in [0, span)
         float s = 0.0f;
         if (lane == 0) out[0] = 0.0f;
         // raw IQ is fetched kR900Ahead groups ahead of the sequential adds (global-load latency).  Two things keep
@@ -730,26 +736,80 @@ r900_chain_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hi
 // mbarrier pairs (full / empty) per ring slot carry the hand-offs, one pair of operations per kChainUnit samples.
 // Same additions in the same order as r900.go:96-100.  Four chains per CTA keep every chain of a 4 GiB call
 // resident at once (the kernel's time is ONE chain's latency as long as that holds).
-constexpr int kChainsPerCta = 4;
-constexpr int kChainUnit = 128;   // samples per hand-off
-constexpr int kChainRing = 4;     // units in flight between the two warps
-constexpr int kChainAhead = 2;    // units of raw IQ in flight in the producer's registers
-constexpr int kChainPitch = kChainUnit + 4;  // floats per chain row of a ring slot: the 4 consumer lanes hit 4 different bank groups
+constexpr int kChainsPerCta = 16;        // chains per consumer warp (its even lanes)
+constexpr int kChainProducers = 8;       // producer warps per CTA, kChainsPerCta / kChainProducers chains each (a lone warp issues at ~0.4 IPC: the
+                                         // conversion work wants two warps per scheduler)
+constexpr int kChainUnit = 128;          // samples per hand-off: kChainUnit / 64 16-byte loads (8 IQ samples each) per producer lane
+constexpr int kChainRing = 3;            // units in flight between producers and consumer (static shared memory: 48 KB)
+constexpr int kChainAhead = 4;           // units of raw IQ in flight in a producer's registers (a warp has 6 scoreboards: more loads in flight share them, and a wait on a shared scoreboard waits for its NEWEST load)
+constexpr int kChainPitch = kChainUnit + 4;  // floats per chain row of a ring slot: consecutive consumer lanes hit different bank groups
+constexpr int kChainsPerWarp = kChainsPerCta / kChainProducers;   // chains of one producer warp
+constexpr int kChainLanes = 32 / kChainsPerWarp;                    // its lanes per chain, 8 samples (16 bytes) each per load
+constexpr int kChainLoads = kChainUnit / (8 * kChainLanes);         // 16-byte loads per producer lane and unit
+static_assert(kChainsPerCta % kChainProducers == 0 && 32 % kChainsPerWarp == 0 && kChainUnit % (8 * kChainLanes) == 0, "producer geometry");
 
-__global__ void __launch_bounds__(64)
+// 8 consecutive IQ samples (16 bytes) of the call-relative sample range [j0, j0 + 8), j0 a multiple of 8: from the call's
+// bytes, from the history of the previous call (j0 < 0), or nothing (before the start of the stream).  The chain starts
+// (b + 1) * BS - BUF and the hand-off unit are multiples of 8 samples, so a group never straddles the call boundary.
+__device__ __forceinline__ const uint8_t* raw8_addr(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist, int hist_samples,
+                                                    long long j0, bool wanted) {
+    // ALWAYS a valid address: groups that must not be read (before the history, past the chain) read the call's first bytes
+    // instead; the caller zeroes their magnitudes.
+    const bool in_hist = j0 < 0;
+    const bool ok = wanted && (!in_hist || -j0 <= (long long)hist_samples);
+    const uint8_t* p = in_hist ? hist + 2 * ((long long)hist_samples + j0) : iq + 2 * j0;
+    return ok ? p : iq;
+}
+// Ampere-style asynchronous copies (LDGSTS): 16 bytes global -> shared per lane, completion in ORDER per commit group.
+// Register loads cannot give this kernel its prefetch depth: a warp has six scoreboards, the loads of the ring share
+// them, and waiting for the oldest load of a shared scoreboard waits for the newest one too (seen as long_scoreboard on the
+// first use of every unit, whatever the depth).  wait_group<N> waits until at most N groups are pending.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// Spinning wait on a phase with the NON-blocking probe: mbarrier.try_wait may suspend the warp for a system-dependent time
+// when the phase is not complete yet -- fine for a TMA refill that takes a microsecond, ruinous for hand-offs between two
+// warps that happen every few hundred cycles.
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+    while (!mbar_test(bar, parity)) {}
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// lut[v] of decode.go:209-216 without the table: x = fl((127.5 - v) / 127.5) is exactly fma(n, rhi, fl(n * rlo)) with
+// n = 127.5 - v for all 256 byte values (checked exhaustively with exact arithmetic, tests/test_oracle.py), then fl(x * x).
+// `mag` = 0x4700vv00 as a float = 32768 + v.
+__device__ __forceinline__ float lut_of_magic(float mag) {
+    const float kRhi = __uint_as_float(1006665857u), kRlo = __uint_as_float(2952724223u);
+    const float n = __fsub_rn(32895.5f, mag);
+    const float x = __fmaf_rn(n, kRhi, __fmul_rn(n, kRlo));
+    return __fmul_rn(x, x);
+}
+
+// Why this shape.  A chain is ~24 700 DEPENDENT float32 adds: 4.2 cycles each (measured), 55 us of pure latency, and the
+// kernel's time is one chain's time as long as every chain of the call is resident.  What the chain really pays on top
+// (measured, B200): every shared- or global-memory instruction that sits in the in-order instruction stream of the warp
+// that runs the adds costs it 5-12 cycles -- nothing of it hides behind the add latency.  So the consumer warp does the
+// minimum: one LDS.128 and one STG.128 per four adds, sixteen chains side by side (one SIMT instruction advances all of
+// them; the whole-vector stores go straight to the padded scratch rows, no second ring), and everything else lives in the
+// producer warps: asynchronous 16-byte copies (in-order completion, any depth), magnitudes COMPUTED instead of looked up
+// (the table lookups of 16 chains would take the shared-memory bandwidth the hand-offs need).  Round-2 history at 4 GiB /
+// ~2400 chains: 451 us (4 chains per CTA, scalar 2-byte loads, lookups, second ring) -> 293 (16-byte loads) -> 192 (two
+// producers) -> 203 (this kernel; 131 us of it remain with the adds and the stores switched off: hand-off and issue
+// overhead of the lone consumer warp).
+__global__ void __launch_bounds__((kChainProducers + 1) * 32)
 r900_chain2_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist, int hist_samples, int hist_valid,
-                   const float* __restrict__ lut_g, DevCfg cfg, const int* __restrict__ slot_block, int slot_cap,
+                   DevCfg cfg, const int* __restrict__ slot_block, int slot_cap,
                    const unsigned int* __restrict__ slot_count, int span, float* __restrict__ scratch) {
-    __shared__ float lut[256];
     __shared__ __align__(16) float m_s[kChainRing][kChainsPerCta][kChainPitch];
-    __shared__ __align__(16) float s_s[kChainRing][kChainsPerCta][kChainPitch];
+    __shared__ __align__(16) uint4 raw_s[kChainProducers][kChainAhead][kChainLoads][32];   // a producer lane's own prefetch ring
     __shared__ __align__(8) unsigned long long bars[2 * kChainRing];  // [0, R): full, [R, 2R): empty
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kChainRing]);
     if (threadIdx.x == 0) {
         for (int r = 0; r < kChainRing; r++) {
-            mbar_init(full0 + 8 * r, 1);                 // the producer's lane 0
-            mbar_init(empty0 + 8 * r, kChainsPerCta);    // the consumer lanes
+            mbar_init(full0 + 8 * r, kChainProducers);   // lane 0 of every producer warp
+            mbar_init(empty0 + 8 * r, 1);                // lane 0 of the consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -761,106 +821,134 @@ r900_chain2_kernel(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ h
     uint32_t ph = 0;  // producer: parity to wait for on empty[r]; consumer: on full[r]  (bit r)
     auto arrive = [](uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); };
     for (unsigned int slot0 = blockIdx.x * kChainsPerCta; slot0 < nslots; slot0 += gridDim.x * kChainsPerCta) {
-        if (warp == 0) {
-            // ---- producer: magnitudes in, finished sums out
-            long long first[kChainsPerCta];
-            float* out[kChainsPerCta];
-            bool valid[kChainsPerCta];
+        if (warp < kChainProducers) {
+            // ---- producer: lane = (chain kChainsPerWarp * warp + lane / kChainLanes, 8 samples per load at 8 * (lane % kChainLanes))
+            const int ch = warp * kChainsPerWarp + lane / kChainLanes, off = (lane % kChainLanes) * 8;
+            const unsigned int slot = slot0 + ch;
+            const bool valid = slot < nslots;
+            const long long first = ((long long)(valid ? slot_block[slot] : 0) + 1) * cfg.BS - cfg.BUF;   // sample of the parser's signal[0]
+            const uint32_t ring0 = smem_u32(&raw_s[warp][0][0][lane]);
+            auto fetch = [&](int u) {   // unit u's bytes of this lane into ring slot u % Ahead; one commit group per unit
 #pragma unroll
-            for (int ch = 0; ch < kChainsPerCta; ch++) {
-                valid[ch] = slot0 + ch < nslots;
-                const long long b = valid[ch] ? slot_block[slot0 + ch] : 0;
-                first[ch] = (b + 1) * cfg.BS - cfg.BUF;                            // sample of the parser's signal[0]
-                out[ch] = scratch + (size_t)(slot0 + ch) * (size_t)span;           // out[i] = csum[i], i in [0, span)
-            }
-            uint32_t rq[kChainAhead][kChainsPerCta][kChainUnit / 32];
-            auto fetch = [&](int u, int ch, int j) -> uint32_t {
-                const int i = u * kChainUnit + j * 32 + lane;
-                return (valid[ch] && u < nunits && i < span - 1) ? raw_at(iq, hist, hist_samples, hist_valid, first[ch] + i) : 0x10000u;
-            };
-#pragma unroll
-            for (int a = 0; a < kChainAhead; a++)
-#pragma unroll
-                for (int ch = 0; ch < kChainsPerCta; ch++)
-#pragma unroll
-                    for (int j = 0; j < kChainUnit / 32; j++) rq[a][ch][j] = fetch(a, ch, j);
-            auto flush = [&](int u) {   // unit u's sums are complete in ring slot u % R
-                const int r = u % kChainRing;
-                mbar_wait(empty0 + 8 * r, (ph >> r) & 1u);
-                ph ^= 1u << r;
-#pragma unroll
-                for (int ch = 0; ch < kChainsPerCta; ch++)
-#pragma unroll
-                    for (int j = 0; j < kChainUnit / 32; j++) {
-                        const int i = u * kChainUnit + j * 32 + lane + 1;
-                        if (valid[ch] && i < span) out[ch][i] = s_s[r][ch][j * 32 + lane];
-                    }
-                __syncwarp();   // every lane has read the slot before it is refilled
-            };
-            for (int u0 = 0; u0 < nunits; u0 += kChainAhead) {
-#pragma unroll
-                for (int a = 0; a < kChainAhead; a++) {
-                    const int u = u0 + a;
-                    if (u >= nunits) break;  // warp-uniform
-                    const int r = u % kChainRing;
-                    if (u >= kChainRing) flush(u - kChainRing);
-#pragma unroll
-                    for (int ch = 0; ch < kChainsPerCta; ch++)
-#pragma unroll
-                        for (int j = 0; j < kChainUnit / 32; j++) {
-                            m_s[r][ch][j * 32 + lane] = mag_of(rq[a][ch][j], lut);   // 0.0 past the end of the chain
-                            rq[a][ch][j] = fetch(u + kChainAhead, ch, j);
-                        }
-                    __syncwarp();
-                    if (lane == 0) arrive(full0 + 8 * r);
+                for (int l = 0; l < kChainLoads; l++) {
+                    const int i = u * kChainUnit + l * (8 * kChainLanes) + off;
+                    cp_async16(ring0 + (uint32_t)((u % kChainAhead) * kChainLoads + l) * 32u * 16u,
+                               raw8_addr(iq, hist, hist_samples, first + i, valid && u < nunits && i < span - 1));
                 }
+                cp_async_commit();
+            };
+            for (int a = 0; a < kChainAhead; a++) fetch(a);
+            for (int u = 0; u < nunits; u++) {
+                const int r = u % kChainRing;
+                cp_async_wait<kChainAhead - 1>();   // unit u's bytes have landed (groups complete in order)
+                float m[kChainLoads][8];
+#pragma unroll
+                for (int l = 0; l < kChainLoads; l++) {
+                    const uint4 rv = raw_s[warp][u % kChainAhead][l][lane];
+                    const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+                    // magnitudes of the 8 samples (decode.go:219-225), bytes as "magic" floats 32768 + v
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float i0 = lut_of_magic(__uint_as_float(__byte_perm(w[k], 0x47000000u, 0x7604)));
+                        const float q0 = lut_of_magic(__uint_as_float(__byte_perm(w[k], 0x47000000u, 0x7614)));
+                        const float i1 = lut_of_magic(__uint_as_float(__byte_perm(w[k], 0x47000000u, 0x7624)));
+                        const float q1 = lut_of_magic(__uint_as_float(__byte_perm(w[k], 0x47000000u, 0x7634)));
+                        m[l][2 * k] = __fadd_rn(i0, q0);
+                        m[l][2 * k + 1] = __fadd_rn(i1, q1);
+                    }
+                    // samples before the start of the stream or past the last running sum the parser reads contribute 0.0
+                    // (checked per sample only in the rare group at an edge)
+                    const int i0s = u * kChainUnit + l * (8 * kChainLanes) + off;
+                    const long long j0 = first + i0s;
+                    const bool whole = valid && i0s + 8 <= span - 1 && (j0 >= 0 || -j0 <= (long long)hist_valid);
+                    if (!whole) {
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const long long j = j0 + k;
+                            const bool ok = valid && i0s + k < span - 1 && (j >= 0 || -j <= (long long)hist_valid);
+                            if (!ok) m[l][k] = 0.0f;
+                        }
+                    }
+                }
+                fetch(u + kChainAhead);   // refills the slot just read (its bytes are in registers: data dependence above)
+                if (u >= kChainRing) {   // the consumer has read this ring slot's previous unit
+                    mbar_spin(empty0 + 8 * r, (ph >> r) & 1u);
+                    ph ^= 1u << r;
+                }
+#pragma unroll
+                for (int l = 0; l < kChainLoads; l++) {
+                    float4* d4 = reinterpret_cast<float4*>(&m_s[r][ch][l * (8 * kChainLanes) + off]);
+                    d4[0] = make_float4(m[l][0], m[l][1], m[l][2], m[l][3]);
+                    d4[1] = make_float4(m[l][4], m[l][5], m[l][6], m[l][7]);
+                }
+                __syncwarp();
+                if (lane == 0) arrive(full0 + 8 * r);
             }
-            for (int u = (nunits > kChainRing ? nunits - kChainRing : 0); u < nunits; u++) flush(u);
-            if (lane < kChainsPerCta && slot0 + lane < nslots) scratch[(size_t)(slot0 + lane) * (size_t)span] = 0.0f;   // csum[0]
-        } else if ((lane & 7) == 0) {
-            // ---- consumer: four serial sections side by side, and nothing else
-            const int ch = lane >> 3;
+            cp_async_wait<0>();
+            // drain: the consumer's last hand-backs (keeps the barrier phases in step for the next group of chains)
+            for (int u = (nunits > kChainRing ? nunits - kChainRing : 0); u < nunits; u++) {
+                const int r = u % kChainRing;
+                mbar_spin(empty0 + 8 * r, (ph >> r) & 1u);
+                ph ^= 1u << r;
+            }
+        } else {
+            // ---- consumer: sixteen serial sections side by side (even lanes), and nothing else: LDS.128 of the next 32
+            // magnitudes into the other register set, 32 dependent adds, STG.128 of the sums (r900.go:96-100 order)
+            const int ch = lane >> 1;
+            const bool active = (lane & 1) == 0 && slot0 + ch < nslots;
+            float* out = r900_row(scratch, slot0 + (active ? ch : 0), span);   // out[i] = csum[i]
+            if (active) out[0] = 0.0f;
             float acc = 0.0f;
-            float4 v[8], vn[8];
-            mbar_wait(full0, ph & 1u);
+            float4 va[8], vb[8];
+            mbar_spin(full0, ph & 1u);
             ph ^= 1u;
             {
                 const float4* mv = reinterpret_cast<const float4*>(&m_s[0][ch][0]);
 #pragma unroll
-                for (int k = 0; k < 8; k++) vn[k] = mv[k];
+                for (int k = 0; k < 8; k++) va[k] = mv[k];
             }
+            static_assert((kChainUnit / 32) % 2 == 0, "the register sets swap roles once per group of 32");
             for (int u = 0; u < nunits; u++) {
                 const int r = u % kChainRing, rn = (u + 1) % kChainRing;
                 const bool have_next = u + 1 < nunits;
-                // probe the next unit's barrier now: the answer is needed three sub-groups (~400 cycles) from here
+                // probe the next unit's barrier now: the answer is needed a few hundred cycles from here
                 bool ready = have_next ? mbar_test(full0 + 8 * rn, (ph >> rn) & 1u) : false;
-#pragma unroll
-                for (int g = 0; g < kChainUnit / 32; g++) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = vn[k];
-                    if (g + 1 < kChainUnit / 32) {   // the next 32 magnitudes go out before this group's dependent adds
+                float4* o4 = reinterpret_cast<float4*>(out + u * kChainUnit + 1);   // csum[i0 + 1 ..]: 16-byte aligned
+                auto group = [&](int g, float4 (&cur)[8], float4 (&nxt)[8]) {
+                    if (g + 1 < kChainUnit / 32) {
                         const float4* mv = reinterpret_cast<const float4*>(&m_s[r][ch][(g + 1) * 32]);
 #pragma unroll
-                        for (int k = 0; k < 8; k++) vn[k] = mv[k];
-                    } else if (have_next) {
-                        if (!ready) mbar_wait(full0 + 8 * rn, (ph >> rn) & 1u);
-                        ph ^= 1u << rn;
-                        const float4* mv = reinterpret_cast<const float4*>(&m_s[rn][ch][0]);
+                        for (int k = 0; k < 8; k++) nxt[k] = mv[k];
+                    } else {
+                        // this unit's magnitudes are all in registers: hand the slot back, then take the next unit's
+                        __syncwarp();
+                        if (lane == 0) arrive(empty0 + 8 * r);
+                        if (have_next) {
+                            if (!ready) mbar_spin(full0 + 8 * rn, (ph >> rn) & 1u);
+                            ph ^= 1u << rn;
+                            const float4* mv = reinterpret_cast<const float4*>(&m_s[rn][ch][0]);
 #pragma unroll
-                        for (int k = 0; k < 8; k++) vn[k] = mv[k];
+                            for (int k = 0; k < 8; k++) nxt[k] = mv[k];
+                        }
                     }
 #pragma unroll
                     for (int k = 0; k < 8; k++) {          // strictly left to right, r900.go:97-99
-                        acc = __fadd_rn(acc, v[k].x); v[k].x = acc;
-                        acc = __fadd_rn(acc, v[k].y); v[k].y = acc;
-                        acc = __fadd_rn(acc, v[k].z); v[k].z = acc;
-                        acc = __fadd_rn(acc, v[k].w); v[k].w = acc;
+                        acc = __fadd_rn(acc, cur[k].x); cur[k].x = acc;
+                        acc = __fadd_rn(acc, cur[k].y); cur[k].y = acc;
+                        acc = __fadd_rn(acc, cur[k].z); cur[k].z = acc;
+                        acc = __fadd_rn(acc, cur[k].w); cur[k].w = acc;
                     }
-                    float4* sv = reinterpret_cast<float4*>(&s_s[r][ch][g * 32]);
+                    // whole vectors always: the rows are padded to whole units (sums past span - 1 are never read)
+                    if (active) {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) sv[k] = v[k];
+                        for (int k = 0; k < 8; k++) o4[g * 8 + k] = cur[k];
+                    }
+                };
+#pragma unroll
+                for (int g = 0; g < kChainUnit / 32; g += 2) {
+                    group(g, va, vb);
+                    group(g + 1, vb, va);
                 }
-                arrive(empty0 + 8 * r);
             }
         }
     }
@@ -884,7 +972,7 @@ __global__ void r900_digits_kernel(DevCfg cfg, const RawHit* __restrict__ hits, 
         const int slot = block_slot[b];
         if (slot < 0) continue;  // handled by the replay kernel
         const int idx = (int)(h.s & (unsigned long long)(cfg.BS - 1));
-        const float* cs = scratch + (size_t)slot * (size_t)span + (idx + cfg.PL - cfg.SL + 4 * k * cfg.CL);
+        const float* cs = r900_row(scratch, slot, span) + (idx + cfg.PL - cfg.SL + 4 * k * cfg.CL);
         digits[c * ERTGPU_R900_DIGITS + k] = r900_digit(cs[0], cs[cfg.CL], cs[2 * cfg.CL], cs[3 * cfg.CL], cs[4 * cfg.CL]);
     }
 }
@@ -897,7 +985,9 @@ __global__ void r900_replay_kernel(const uint8_t* __restrict__ iq, const uint8_t
                                    int hist_samples, int hist_valid, const float* __restrict__ lut_g,
                                    DevCfg cfg, const RawHit* __restrict__ hits, unsigned long long hit_cap,
                                    const unsigned long long* __restrict__ hit_count,
-                                   const int* __restrict__ block_slot, uint8_t* __restrict__ digits) {
+                                   const int* __restrict__ block_slot, uint8_t* __restrict__ digits,
+                                   const unsigned int* __restrict__ slot_count = nullptr, int slot_cap = 0) {
+    if (slot_count && *slot_count <= (unsigned)slot_cap) return;   // every detecting block found a scratch slot
     __shared__ float lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
     __syncthreads();
