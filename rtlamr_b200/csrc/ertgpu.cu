@@ -29,6 +29,7 @@
 #include "demod_generic.cuh"
 #include "ert_common.cuh"
 #include "search.cuh"
+#include "r900_tmem.cuh"
 #include "synth.cuh"
 
 using namespace ert;
@@ -84,7 +85,7 @@ struct ertgpu_handle {
     bool search_legacy = false; // env ERTGPU_SEARCH_LEGACY: the per-bit-load Search kernel (kept for chip lengths like 78 and as a cross-check)
     int sm_count = 148;
     bool use_pdl = true;      // env ERTGPU_PDL=0: ordinary launches for Search and Slice
-    int r900_chain_mode = 0;  // env ERTGPU_R900_CHAIN: (default) two-warp pipeline; "smem" = one warp, serial lane 0; "shfl" = one warp, shuffled sums
+    int r900_chain_mode = 0;  // env ERTGPU_R900_CHAIN: (default) producer/consumer warps through shared memory; "tmem" = Tensor Memory between the stages; "smem" = one warp, serial lane 0; "shfl" = one warp, shuffled sums
 
     // state of the last enqueued pipeline (for fetch and taps)
     bool pending = false;       // a pipeline is enqueued and not yet synchronised
@@ -398,7 +399,12 @@ int enqueue_pipeline(ertgpu_handle* h, const uint8_t* d_iq, int64_t nblocks, uin
             r900_chain_kernel<false><<<148 * 16, kR900ChainWarps * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, h->d_lut, c,
                                                                        h->d_slot_block, h->r900_slots, h->d_slot_count,
                                                                        h->r900_span, h->d_r900_scratch);
-        } else {   // default: producer / consumer warps per chain
+        } else if (h->r900_chain_mode == 3) {   // Tensor Memory between the stages (r900_tmem.cuh): exact, measured no faster (212 vs 203 us)
+            static OncePerDevice t3_once;
+            if (t3_once.first(current_device())) CUDA_TRY(h, cudaFuncSetAttribute(r900_chain3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
+            r900_chain3_kernel<<<(unsigned)h->sm_count * 2, kT3Warps * 32, kT3SmemBytes, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, c, h->d_slot_block,
+                                                        h->r900_slots, h->d_slot_count, h->r900_span, h->d_r900_scratch);
+        } else {   // default: producer warps + one consumer warp per 16 chains, hand-offs through shared memory
             r900_chain2_kernel<<<(unsigned)h->sm_count * 2, (kChainProducers + 1) * 32, 0, st>>>(d_iq, hist, c.hist_samples, h->hist_valid, c, h->d_slot_block,
                                                         h->r900_slots, h->d_slot_count, h->r900_span, h->d_r900_scratch);
         }
@@ -793,7 +799,7 @@ static int allocate_impl(ertgpu_handle* h, int32_t device, int64_t max_blocks_pe
     if (const char* e = getenv("ERTGPU_FAST_WARPS")) h->demod_warps = atoi(e);   // 100 * VAR + W, see launch_demod_fast
     if (const char* e = getenv("ERTGPU_SEARCH_LEGACY")) h->search_legacy = atoi(e) != 0;
     if (const char* e = getenv("ERTGPU_PDL")) h->use_pdl = atoi(e) != 0;
-    if (const char* e = getenv("ERTGPU_R900_CHAIN")) h->r900_chain_mode = strcmp(e, "shfl") == 0 ? 2 : (strcmp(e, "smem") == 0 ? 1 : 0);
+    if (const char* e = getenv("ERTGPU_R900_CHAIN")) h->r900_chain_mode = strcmp(e, "shfl") == 0 ? 2 : (strcmp(e, "smem") == 0 ? 1 : (strcmp(e, "tmem") == 0 ? 3 : 0));
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
     if (h->sm_count < 1) h->sm_count = 148;
     h->cur_plane = h->cur_hist = 0;

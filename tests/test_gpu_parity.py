@@ -170,7 +170,7 @@ def test_r900_chain_shuffle_form_agrees(built, monkeypatch, mt, cl):
     iq, _, _ = synth_stream(mt, cl, 1 << 21, spacing=1 << 18)
     o, cands, msgs = oracle_run(mt, cl, iq)
     out = {}
-    for form in ("shfl", "smem", "pipe"):     # pipe = the default two-warp producer / consumer chain
+    for form in ("shfl", "smem", "pipe", "tmem"):     # pipe = the default producer / consumer chain; tmem = Tensor Memory between the stages
         monkeypatch.setenv("ERTGPU_R900_CHAIN", form)
         h = capi.new_decoder(mt, cl)
         got = h.decode(whole_blocks(iq, h.cfg.block_size2))
@@ -178,7 +178,7 @@ def test_r900_chain_shuffle_form_agrees(built, monkeypatch, mt, cl):
         out[form] = np.sort(got, order=["block", "idx", "preamble_id"])
         h.close()
     assert (out["shfl"]["flags"] & capi.CAND_HAS_R900).any()
-    assert out["shfl"].tobytes() == out["smem"].tobytes() == out["pipe"].tobytes()
+    assert out["shfl"].tobytes() == out["smem"].tobytes() == out["pipe"].tobytes() == out["tmem"].tobytes()
     assert (out["shfl"]["check_mask"] != 0).any()
 
 
