@@ -1,10 +1,11 @@
 """Turn the ncu artefacts a gpurun call left in gpurun_out/ into the tracked summaries under profiles/.
 
 Inputs (produced on the GPU box):
-  gpurun_out/bench_r1.json        python bench.py --steps 30 --warmup 3
-  gpurun_out/bench_r1_ref.json    python bench.py --impl reference --steps 3 --warmup 1
-  gpurun_out/launches_r1.csv      ncu --metrics gpu__time_duration.sum --clock-control none --csv ... bench.py --steps 2 --warmup 1
-  gpurun_out/prof_r1_final.ncu-rep  ncu --set full --clock-control none --import-source on -k regex:... bench.py --steps 2 --warmup 1
+  (TAG = r1, r2, ...: `python tools/make_profiles.py TAG`)
+  gpurun_out/bench_TAG.json        python bench.py --steps 30 --warmup 3
+  gpurun_out/bench_TAG_ref.json    python bench.py --impl reference --steps 3 --warmup 1
+  gpurun_out/launches_TAG.csv      ncu --metrics gpu__time_duration.sum --clock-control none --csv ... bench.py --steps 2 --warmup 1
+  gpurun_out/prof_TAG_final.ncu-rep  ncu --set full --clock-control none --import-source on -k regex:... bench.py --steps 2 --warmup 1
 """
 import collections, csv, json, os, re, subprocess, sys
 
@@ -62,14 +63,14 @@ def to_bytes(s):
 
 d = kern[0]
 rd, wr, ns = to_bytes(d["dram_read"]), to_bytes(d["dram_write"]), 536870912
-json.dump({"kernel": "demod_fast_kernel<72,8>", "source": f"ncu --set full, profiles/{tag}_kernels.json (1 GiB launch)",
+json.dump({"kernel": re.sub(r"\(.*", "", d["kernel"]).replace("void ert::", "").strip(), "source": f"ncu --set full, profiles/{tag}_kernels.json (1 GiB launch)",
            "dram_bytes_read": rd, "dram_bytes_write": wr, "samples_per_launch": ns, "dram_bytes_per_sample": (rd + wr) / ns},
           open(os.path.join(P, "demod_traffic.json"), "w"), indent=1)
-for f in ("bench_r1.json", "bench_r1_ref.json"):
+for f in (f"bench_{tag}.json", f"bench_{tag}_ref.json"):
     src = os.path.join(G, f)
     if os.path.exists(src):
         line = [l for l in open(src) if l.startswith("{")][-1]
-        open(os.path.join(P, f.replace("bench_r1", f"{tag}_bench_line")), "w").write(line)
+        open(os.path.join(P, f.replace(f"bench_{tag}", f"{tag}_bench_line")), "w").write(line)
 open(os.path.join(P, f"{tag}_launches.csv"), "w").write(open(os.path.join(G, f"launches_{tag}.csv")).read())
 open(os.path.join(P, f"{tag}_launch_table.md"), "w").write(tbl + "\n")
 print(tbl)
