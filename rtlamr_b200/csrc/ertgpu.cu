@@ -22,6 +22,9 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -33,6 +36,76 @@
 #include "synth.cuh"
 
 using namespace ert;
+
+// Host threads that copy a pageable buffer into a pinned one in parallel.  Persistent: starting a std::thread costs
+// 30-50 us, a 32 MiB chunk takes ~0.7 ms to copy with 8 threads -- spawning them per chunk (round 2's first form) made
+// 8 threads slower than 4.  One pool per handle, created on the first pageable call.
+class CopyPool {
+public:
+    explicit CopyPool(int nworkers) {
+        for (int i = 0; i < nworkers; i++) workers_.emplace_back([this, i] { run(i + 1); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    int size() const { return (int)workers_.size() + 1; }
+    // dst[0, n) = src[0, n) on the calling thread + the workers; returns when every part is done
+    void copy(uint8_t* dst, const uint8_t* src, size_t n) {
+        const size_t kMin = 1u << 20;
+        const int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)size(), (n + kMin - 1) / kMin));
+        const size_t per = (((n + (size_t)parts - 1) / (size_t)parts) + 4095) & ~(size_t)4095;
+        if (parts > 1) {
+            std::lock_guard<std::mutex> g(m_);
+            dst_ = dst; src_ = src; n_ = n; per_ = per; parts_ = parts;
+            pending_ = parts - 1;
+            gen_++;
+        }
+        if (parts > 1) cv_.notify_all();
+        memcpy(dst, src, std::min(n, per));
+        if (parts > 1) {
+            std::unique_lock<std::mutex> g(m_);
+            done_.wait(g, [this] { return pending_ == 0; });
+        }
+    }
+
+private:
+    void run(int part) {
+        unsigned long long seen = 0;
+        for (;;) {
+            uint8_t* dst; const uint8_t* src; size_t n, per; int parts;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                dst = dst_; src = src_; n = n_; per = per_; parts = parts_;
+            }
+            if (part >= parts) continue;
+            const size_t a = std::min(n, per * (size_t)part), b = std::min(n, per * (size_t)(part + 1));
+            if (b > a) memcpy(dst + a, src + a, b - a);
+            {
+                std::lock_guard<std::mutex> g(m_);
+                pending_--;
+            }
+            done_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+    uint8_t* dst_ = nullptr;
+    const uint8_t* src_ = nullptr;
+    size_t n_ = 0, per_ = 0;
+    int parts_ = 0, pending_ = 0;
+};
 
 struct ertgpu_handle {
     std::string err;
@@ -61,6 +134,7 @@ struct ertgpu_handle {
     size_t stage_bytes = 0;
     uint8_t* h_stage[2] = {nullptr, nullptr};  // pinned staging of pageable input (allocated on first use)
     size_t h_stage_bytes = 0;
+    std::unique_ptr<CopyPool> copy_pool;   // host threads of the pageable-input staging
     std::string kernels;                        // instantiations launched by the last pipeline
     RawHit* d_hits = nullptr;
     HitWord* d_words = nullptr;       // words of starts that hold a hit (what Slice works from)
@@ -515,25 +589,6 @@ int deliver(ertgpu_handle* h, ertgpu_candidate* out, size_t cap, size_t* n_out) 
     return ERTGPU_OK;
 }
 
-// memcpy on up to `nthreads` host threads (one memcpy stream does not fill the memory bus of a server CPU)
-void parallel_copy(uint8_t* dst, const uint8_t* src, size_t n, int nthreads) {
-    const size_t kMin = 4u << 20;
-    int t = (int)std::min<size_t>((size_t)nthreads, (n + kMin - 1) / kMin);
-    if (t <= 1) {
-        memcpy(dst, src, n);
-        return;
-    }
-    std::vector<std::thread> th;
-    th.reserve((size_t)t - 1);
-    const size_t per = ((n / (size_t)t) + 4095) & ~(size_t)4095;
-    for (int i = 1; i < t; i++) {
-        const size_t a = std::min(n, per * (size_t)i), b = std::min(n, per * (size_t)(i + 1));
-        if (b > a) th.emplace_back([=] { memcpy(dst + a, src + a, b - a); });
-    }
-    memcpy(dst, src, std::min(n, per));
-    for (auto& x : th) x.join();
-}
-
 void begin_call(ertgpu_handle* h) {
     h->results.clear();
     h->uncopied = false;
@@ -913,8 +968,11 @@ int ertgpu_decode(ertgpu_handle* h, const uint8_t* iq, size_t nbytes, uint32_t f
         for (int k = 0; k < 2; k++) CUDA_TRY(h, cudaHostAlloc(&h->h_stage[k], h->stage_bytes, cudaHostAllocDefault));
         h->h_stage_bytes = h->stage_bytes;
     }
-    int copy_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 4));  // ~6 GB/s per memcpy stream; 8 fill a PCIe 5 x16 link
-    if (const char* e = getenv("ERTGPU_STAGE_THREADS")) copy_threads = std::min(64, std::max(1, atoi(e)));
+    if (pageable) {
+        int copy_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 4));  // ~6 GB/s per memcpy stream; 8 fill a PCIe 5 x16 link
+        if (const char* e = getenv("ERTGPU_STAGE_THREADS")) copy_threads = std::min(64, std::max(1, atoi(e)));
+        if (!h->copy_pool || h->copy_pool->size() != copy_threads) h->copy_pool.reset(new CopyPool(copy_threads - 1));
+    }
     int64_t done = 0, launches = 0;
     for (int64_t i = 0; done < nblocks; i++) {
         const int k = (int)(i & 1);
@@ -923,7 +981,7 @@ int ertgpu_decode(ertgpu_handle* h, const uint8_t* iq, size_t nbytes, uint32_t f
         const uint8_t* src = iq + (size_t)done * bs2;
         const size_t nbytes_chunk = (size_t)nb * bs2;
         if (pageable) {
-            parallel_copy(h->h_stage[k], src, nbytes_chunk, copy_threads);
+            h->copy_pool->copy(h->h_stage[k], src, nbytes_chunk);
             src = h->h_stage[k];
         }
         CUDA_TRY(h, cudaMemcpyAsync(h->d_stage[k], src, nbytes_chunk, cudaMemcpyHostToDevice, h->copy_stream));
