@@ -30,6 +30,23 @@ def test_plan_properties():
     assert shard.plan(100, 1, 4096, 13824)[0].owns_start(4096 * 10, 4096, 17920)
 
 
+def test_c_abi_plan_equals_python_plan(built):
+    """ertgpu_plan_shards (the product's plan, rtlamr_b200/csrc/sharded.cpp) against the Python mirror the ranks of bench.py
+    use, for every stock geometry and random stream lengths / shard counts; bad requests are refused.  No GPU involved."""
+    from rtlamr_b200 import capi
+    rng = np.random.default_rng(11)
+    geoms = [(4096, 13824), (8192, 105984), (8192, 16704), (4096, 14976), (2048, 6144)]
+    for bs, pkl in geoms:
+        for _ in range(40):
+            total = int(rng.integers(0, 1 << 20))
+            n = int(rng.integers(1, 17))
+            want = [(p.first_block, p.last_block, p.first_fed_block) for p in shard.plan(total, n, bs, pkl)]
+            assert [tuple(p) for p in capi.plan_shards(total, n, bs, pkl)] == want
+    for bad in ((-1, 2, 4096, 13824), (10, 0, 4096, 13824), (10, 2, 0, 13824)):
+        with pytest.raises(capi.ErtGpuError):
+            capi.plan_shards(*bad)
+
+
 def _worker(rank, world, port, path):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
