@@ -750,7 +750,10 @@ int launch_demod_fast_cw(const uint8_t* iq, const uint8_t* hist, int hist_sample
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return (int)cudaErrorNotSupported;
     // the descriptor only depends on (base, rows, row length, box): calls that stream through the same
-    // staging buffer reuse it
+    // staging buffer reuse it.  Invariant: the key is everything the encoded map contains -- a buffer that was freed and
+    // re-allocated at the same address with the same number of blocks and block size gives a byte-identical descriptor (a
+    // tensor map holds addresses and extents, no handle to the allocation), so a stale hit cannot exist; the cache is per
+    // thread and per template instantiation (the box is part of the type), and the L2 promotion knob is read once per process.
     struct MapKey { const void* iq; long long nblocks; int BS; };
     static thread_local MapKey last_key = {nullptr, 0, 0};
     static thread_local CUtensorMap map;
