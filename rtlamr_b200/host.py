@@ -56,6 +56,12 @@ def lib():
         L.erthost_parse_dedup.restype = C.c_longlong
         L.erthost_parse_dedup.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.POINTER(_Msg), C.c_longlong,
                                           C.POINTER(C.c_longlong)]
+        L.erthost_parse_filtered.restype = C.c_longlong
+        L.erthost_parse_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
+                                             C.POINTER(_Msg), C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+        L.erthost_encode.restype = C.c_longlong
+        L.erthost_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_int, C.c_longlong, C.c_int,
+                                     C.c_int, C.c_char_p, C.c_longlong]
         _lib = L
     return _lib
 
@@ -106,6 +112,38 @@ def _parse_dedup(self, cands: np.ndarray, block_dedup: bool = True, cap: int = 4
 
 
 Parsers.parse_dedup = _parse_dedup
+
+
+def _parse_filtered(self, cands, filterid: str = "", filtertype: str = "", unique: bool = False, block_dedup: bool = True,
+                    cap: int = 1 << 16):
+    """erthost_parse_filtered: parsers, then the receive loop's filter chain (-filterid, -filtertype, -unique in the order
+    flag.Visit adds them, main.go:97-113) and the cross-block dedup (main.go:236-260).  Returns (messages, dropped by the
+    dedup, rejected by the filters)."""
+    cands = np.ascontiguousarray(cands)
+    out = (_Msg * cap)()
+    dup, flt = C.c_longlong(0), C.c_longlong(0)
+    n = self._L.erthost_parse_filtered(self._h, cands.ctypes.data, len(cands), filterid.encode(), filtertype.encode(),
+                                       1 if unique else 0, 1 if block_dedup else 0, out, cap, C.byref(dup), C.byref(flt))
+    if n < 0:
+        raise RuntimeError(self._L.erthost_error(self._h).decode())
+    return _messages(out, min(n, cap)), int(dup.value), int(flt.value)
+
+
+def _encode(self, cands, fmt: str = "plain", unix_seconds: int = 0, nanos: int = 0, offset: int = 0, length: int = 0,
+            sample_file_is_devnull: bool = True) -> str:
+    """erthost_encode: every parsed message through the plain or csv encoder (flags.go:140-151) as one string of lines."""
+    cands = np.ascontiguousarray(cands)
+    cap = 1 << 22
+    buf = C.create_string_buffer(cap)
+    n = self._L.erthost_encode(self._h, cands.ctypes.data, len(cands), 1 if fmt == "csv" else 0, unix_seconds, nanos, offset, length,
+                               1 if sample_file_is_devnull else 0, buf, cap)
+    if n < 0 or n >= cap:
+        raise RuntimeError("erthost_encode failed" if n < 0 else "encode buffer too small")
+    return buf.value.decode()
+
+
+Parsers.parse_filtered = _parse_filtered
+Parsers.encode = _encode
 
 
 class Receiver:

@@ -133,6 +133,73 @@ long long erthost_parse_dedup(erthost* h, const ertgpu_candidate* cands, long lo
     }
 }
 
+// erthost_parse, then the receive loop of main.go:236-260 on the result with a fresh memory: the filter chain in the order
+// flag.Visit builds it (main.go:97-113: filterid, filtertype, unique -- lexicographic, whatever the command line's order),
+// then the cross-block digest dedup.  filterid / filtertype: comma lists as for the flags, NULL or "" = flag not given.
+long long erthost_parse_filtered(erthost* h, const ertgpu_candidate* cands, long long n, const char* filterid, const char* filtertype,
+                                 int unique, int block_dedup, erthost_msg* out, long long cap, long long* duplicates,
+                                 long long* filtered) {
+    try {
+        std::vector<protocol::MessagePtr> msgs;
+        h->d.Dispatch(cands, (size_t)n, msgs);
+        receiver::FilterChain fc;
+        if (filterid && *filterid) {
+            auto f = std::make_shared<receiver::MeterIDFilter>();
+            f->ids.Set(filterid);
+            fc.Add(f);
+        }
+        if (filtertype && *filtertype) {
+            auto f = std::make_shared<receiver::MeterTypeFilter>();
+            f->types.Set(filtertype);
+            fc.Add(f);
+        }
+        if (unique) fc.Add(std::make_shared<receiver::UniqueFilter>());
+        receiver::BlockDedup dd;
+        receiver::Stats st;
+        std::vector<const protocol::Message*> order;
+        dd.Filter(msgs, block_dedup != 0, [&](const protocol::Message& m) { order.push_back(&m); }, st, fc.empty() ? nullptr : &fc);
+        if (duplicates) *duplicates = st.duplicates;
+        if (filtered) *filtered = st.filtered;
+        std::vector<protocol::MessagePtr> view;
+        for (const protocol::Message* m : order)
+            for (auto& p : msgs)
+                if (p.get() == m) {
+                    view.push_back(std::move(p));
+                    break;
+                }
+        return fill_msgs(view, out, cap);
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return -1;
+    }
+}
+
+// The encoders (flags.go:140-151) on every message of erthost_parse: format 0 = plain (PlainEncoder, flags.go:261-272),
+// 1 = csv (csv/csv.go:27-38); the LogMessage fields (parse.go:103-109) are the caller's.  Returns the number of bytes the
+// lines need (they are written when they fit `cap`), or -1.
+long long erthost_encode(erthost* h, const ertgpu_candidate* cands, long long n, int format, long long unix_seconds, int nanos,
+                         long long offset, int length, int sample_file_is_devnull, char* buf, long long cap) {
+    try {
+        std::vector<protocol::MessagePtr> msgs;
+        h->d.Dispatch(cands, (size_t)n, msgs);
+        std::string all;
+        for (auto& m : msgs) {
+            receiver::LogMessage lm;
+            lm.unix_seconds = unix_seconds;
+            lm.nanos = nanos;
+            lm.Offset = offset;
+            lm.Length = length;
+            lm.Message = m.get();
+            all += format == 1 ? receiver::CsvLine(lm.Record()) : receiver::PlainLine(lm, sample_file_is_devnull != 0) + "\n";
+        }
+        if ((long long)all.size() < cap && buf) memcpy(buf, all.c_str(), all.size() + 1);
+        return (long long)all.size();
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return -1;
+    }
+}
+
 long long erthost_decode(erthost* h, const uint8_t* iq, size_t len, erthost_msg* out, long long cap) {
     try {
         auto msgs = h->d.Decode(iq, len);

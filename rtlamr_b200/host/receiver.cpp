@@ -40,11 +40,11 @@ Receiver::~Receiver() {
 
 void Receiver::Filter(std::vector<protocol::MessagePtr>& msgs, bool block_dedup,
                       const std::function<void(const protocol::Message&)>& emit, Stats& st) {
-    dedup_.Filter(msgs, block_dedup, emit, st);
+    dedup_.Filter(msgs, block_dedup, emit, st, fc_.empty() ? nullptr : &fc_);
 }
 
 void BlockDedup::Filter(std::vector<protocol::MessagePtr>& msgs, bool block_dedup,
-                        const std::function<void(const protocol::Message&)>& emit, Stats& st) {
+                        const std::function<void(const protocol::Message&)>& emit, Stats& st, FilterChain* fc) {
     // main.go:221-224,244-260,292: `next` collects the digests of the current block, a message whose digest
     // was seen in the previous block is skipped, and the maps swap after every block -- including blocks
     // without messages, which is why a gap in the block numbers empties `prev`.
@@ -54,6 +54,10 @@ void BlockDedup::Filter(std::vector<protocol::MessagePtr>& msgs, bool block_dedu
         if (b != prev_block_ + 1) prev_.clear();
         std::set<Digest> next;
         for (; i < msgs.size() && msgs[i]->Block == b; i++) {
+            if (fc && !fc->Match(*msgs[i])) {   // main.go:236-239: rejected before the digest is recorded
+                st.filtered++;
+                continue;
+            }
             Digest dg = NewDigest(*msgs[i]);
             next.insert(dg);
             if (block_dedup && prev_.count(dg)) {

@@ -15,6 +15,7 @@
 #include <tuple>
 #include <vector>
 
+#include "filters.hpp"
 #include "protocol.hpp"
 
 namespace receiver {
@@ -24,7 +25,7 @@ using Digest = std::tuple<std::string, uint8_t, uint32_t, std::vector<uint8_t>>;
 Digest NewDigest(const protocol::Message& m);
 
 struct Stats {
-    int64_t blocks = 0, bytes = 0, messages = 0, duplicates = 0;
+    int64_t blocks = 0, bytes = 0, messages = 0, duplicates = 0, filtered = 0;
     double seconds = 0;
 };
 
@@ -32,9 +33,10 @@ struct Stats {
 // reported for the previous block is dropped; a gap in the block numbers empties the memory.
 class BlockDedup {
 public:
-    // msgs grouped by ascending Block (what Decode returns); `emit` sees every message that is reported.
+    // msgs grouped by ascending Block (what Decode returns); `emit` sees every message that is reported.  `fc` is the
+    // receive loop's filter chain (main.go:236-239): a message it rejects is skipped BEFORE its digest is recorded.
     void Filter(std::vector<protocol::MessagePtr>& msgs, bool block_dedup,
-                const std::function<void(const protocol::Message&)>& emit, Stats& st);
+                const std::function<void(const protocol::Message&)>& emit, Stats& st, FilterChain* fc = nullptr);
     void Reset() {
         prev_.clear();
         prev_block_ = -2;
@@ -52,6 +54,7 @@ public:
     ~Receiver();
 
     protocol::Decoder& decoder() { return d_; }
+    FilterChain& filters() { return fc_; }   // -filterid / -filtertype / -unique (flags.go:147-170)
 
     // Run over a FILE* until EOF.  `emit` is called once per reported message (after the cross-block dedup when block_dedup).
     Stats Run(FILE* in, bool block_dedup, const std::function<void(const protocol::Message&)>& emit);
@@ -70,6 +73,7 @@ private:
     uint8_t* buf_[2] = {nullptr, nullptr};
     size_t buf_bytes_ = 0;
     BlockDedup dedup_;
+    FilterChain fc_;
 };
 
 }  // namespace receiver

@@ -128,6 +128,101 @@ def test_cross_block_dedup_rule_on_the_cpu(built):
     p.close()
 
 
+def test_filter_chain_on_the_cpu(built):
+    """flags.go:226-259 + parse.go:126-149 + main.go:236-260 in the C++ mirror, no device: -filterid, -filtertype and -unique
+    on the oracle's candidates of a synthetic stream, against the same rules applied in Python to the unfiltered messages
+    (chain order filterid, filtertype, unique; a rejected message leaves no digest behind)."""
+    from rtlamr_b200 import host, synth
+    mt, cl = "scm,scm+,idm", 72
+    o = oracle.Oracle(mt, cl)
+    n = 1 << 22
+    pk, truth = synth.make_packets(mt, cl, n, seed=5, spacing=1 << 17)
+    iq = whole_blocks(synth.host_fill(0, n, 0x5EED0001, pk), o.cfg.block_size2)
+    cands, msgs = o.decode(iq)
+    one = _cand_records(cands)
+    # the same transmissions three times, far apart in block numbers: every meter repeats its checksum (what -unique drops)
+    gap = int(one["block"].max()) + 3
+    rec = np.concatenate([one, one, one])
+    rec["block"][len(one):2 * len(one)] += gap
+    rec["block"][2 * len(one):] += 2 * gap
+    p = host.Parsers(mt, cl)
+    allm, _ = p.parse_dedup(rec, block_dedup=False)
+    assert len(allm) == 3 * len(msgs) > 60
+    ids = sorted({m.meter_id for m in allm})
+    types = sorted({m.meter_type for m in allm})
+    want_ids, want_types = ids[::2], types[:1]
+
+    def model(filterid, filtertype, unique, block_dedup):
+        last, out, rejected, dropped = {}, [], 0, 0
+        prev, prev_block, i = set(), -2, 0
+        while i < len(allm):
+            b = allm[i].block
+            if b != prev_block + 1:
+                prev = set()
+            nxt = set()
+            while i < len(allm) and allm[i].block == b:
+                m = allm[i]
+                i += 1
+                ok = (not filterid or m.meter_id in filterid) and (not filtertype or m.meter_type in filtertype)
+                if ok and unique:
+                    if last.get(m.meter_id) == m.checksum:
+                        ok = False
+                    else:
+                        last[m.meter_id] = m.checksum
+                if not ok:
+                    rejected += 1
+                    continue
+                dg = (m.msgtype, m.meter_type, m.meter_id, m.checksum)
+                nxt.add(dg)
+                if block_dedup and dg in prev:
+                    dropped += 1
+                    continue
+                out.append(m)
+            prev, prev_block = nxt, b
+        return out, dropped, rejected
+
+    for fid, ftype, uniq, dd in [(want_ids, [], False, True), ([], want_types, False, True), (want_ids, want_types, True, True),
+                                 ([], [], True, False), ([], [], True, True), (ids, types, False, False)]:
+        got, dropped, rejected = p.parse_filtered(rec, ",".join(map(str, fid)), ",".join(map(str, ftype)), uniq, dd)
+        want, wdropped, wrejected = model(set(fid), set(ftype), uniq, dd)
+        assert [(m.block, m.idx, m.text) for m in got] == [(m.block, m.idx, m.text) for m in want]
+        assert (dropped, rejected) == (wdropped, wrejected)
+    # -unique alone: every meter is reported once per distinct checksum run
+    got, _, rejected = p.parse_filtered(rec, unique=True, block_dedup=False)
+    assert rejected > 0 and len(got) + rejected == len(allm)
+    with pytest.raises(RuntimeError):
+        p.parse_filtered(rec, filterid="12,x")      # strconv.ParseUint error (flags.go:213-217)
+    p.close()
+
+
+def test_plain_and_csv_encoders_on_the_cpu(built, sample_iq):
+    """parse.go:103-129 (LogMessage), flags.go:261-272 (PlainEncoder), csv/csv.go:27-38 over encoding/csv's rules: the lines
+    the C++ mirror prints for the golden capture's messages against lines built here from each message's String() / Record()."""
+    import csv
+    import io
+    from rtlamr_b200 import host
+    mt, cl = "scm", 78
+    o = oracle.Oracle(mt, cl, oracle.SEARCH_EXACT)
+    cands, msgs = o.decode(whole_blocks(sample_iq, o.cfg.block_size2))
+    rec = _cand_records(cands)
+    p = host.Parsers(mt, cl)
+    allm, _ = p.parse_dedup(rec, block_dedup=False)
+    assert len(allm) == len(msgs) >= 14      # the parser's own per-block dedup leaves the 14 golden messages
+    t, ns, off, ln = 1700000000, 123456000, 4096, 8192          # 2023-11-14T22:13:20.123456Z
+    plain = p.encode(rec, "plain", t, ns, off, ln, True).splitlines()
+    plain_off = p.encode(rec, "plain", t, ns, off, ln, False).splitlines()
+    assert plain == ["{Time:2023-11-14T22:13:20.123 SCM:%s}" % m.text for m in allm]
+    assert plain_off == ["{Time:2023-11-14T22:13:20.123 Offset:4096 Length:8192 SCM:%s}" % m.text for m in allm]
+    buf = io.StringIO()
+    w = csv.writer(buf, lineterminator="\n", quoting=csv.QUOTE_MINIMAL)
+    for m in allm:
+        w.writerow(["2023-11-14T22:13:20.123456Z", "4096", "8192", *m.record])
+    assert p.encode(rec, "csv", t, ns, off, ln) == buf.getvalue()
+    # whole seconds: RFC3339Nano drops the fraction
+    assert p.encode(rec, "csv", t, 0, 0, 0).startswith("2023-11-14T22:13:20Z,0,0," + ",".join(allm[0].record) + "\n")
+    p.close()
+
+
 def test_parsers_alone_on_the_golden_capture(built, sample_iq):
     """sample.bin at chip length 78, exact Search: the 853 oracle candidates give the 14 golden messages and rtlamr's
     plain formatting (scm.go:139-143)."""
