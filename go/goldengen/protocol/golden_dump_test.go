@@ -3,7 +3,7 @@
 // Drop this file into <rtlamr>/protocol/ (package protocol: it reads the unexported csum / packed
 // buffers) and run, on any machine with Go, from the rtlamr checkout:
 //
-//	GOLDEN_IN=assets/sample.bin GOLDEN_OUT=/tmp/go_dump_sample_cl78_scm.jsonl \
+//	GOLDEN_IN=$PWD/assets/sample.bin GOLDEN_OUT=/tmp/go_dump_sample_cl78_scm.jsonl \   (absolute: the test runs in ./protocol)
 //	GOLDEN_MSGTYPES=scm GOLDEN_CL=78 go test ./protocol -run TestDumpGolden -count=1
 //
 // (tests/golden/make_go_golden.sh in the rtlamr_b200 repository runs every case the parity loader

@@ -23,8 +23,9 @@ run() {  # name input msgtypes chiplength
   GOLDEN_IN=$2 GOLDEN_OUT="$HERE/go_dump_$1.jsonl" GOLDEN_MSGTYPES=$3 GOLDEN_CL=$4 go test ./protocol -run TestDumpGolden -count=1
   go run ./cmd/goldengen -in "$2" -msgtype "$3" -symbollength "$4" > "$HERE/go_msgs_$1.jsonl"
 }
-run sample_cl78_scm assets/sample.bin scm 78
-run sample_cl72_scm assets/sample.bin scm 72
+# absolute paths: `go test ./protocol` runs the test binary inside the package directory
+run sample_cl78_scm "$PWD/assets/sample.bin" scm 78
+run sample_cl72_scm "$PWD/assets/sample.bin" scm 72
 run synth_cl72_scm "$WORK/synth_cl72_scm.bin" scm 72
 run synth_cl72_multi "$WORK/synth_cl72_multi.bin" scm,scm+,idm 72
 run synth_cl72_r900 "$WORK/synth_cl72_r900.bin" r900 72
