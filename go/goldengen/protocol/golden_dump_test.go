@@ -3,11 +3,11 @@
 // Drop this file into <rtlamr>/protocol/ (package protocol: it reads the unexported csum / packed
 // buffers) and run, on any machine with Go, from the rtlamr checkout:
 //
-//	GOLDEN_IN=$PWD/assets/sample.bin GOLDEN_OUT=/tmp/go_dump_sample_cl78_scm.jsonl \   (absolute: the test runs in ./protocol)
+//	GOLDEN_IN=$PWD/assets/sample.bin GOLDEN_OUT=/tmp/go_dump_sample_cl78_scm.jsonl \
 //	GOLDEN_MSGTYPES=scm GOLDEN_CL=78 go test ./protocol -run TestDumpGolden -count=1
 //
-// (tests/golden/make_go_golden.sh in the rtlamr_b200 repository runs every case the parity loader
-// knows about).  The output is JSON lines:
+// (GOLDEN_IN must be absolute: `go test` runs the test binary inside ./protocol.  tests/golden/make_go_golden.sh in the
+// rtlamr_b200 repository runs every case the parity loader knows about).  The output is JSON lines:
 //
 //	{"kind":"config", ...PacketConfig after Allocate...}
 //	{"kind":"cand","block":B,"preamble":"1111...","idx":I,"bytes":"hex"}      every Data of every Decode call
